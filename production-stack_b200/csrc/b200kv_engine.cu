@@ -1,0 +1,1184 @@
+// b200kv_engine.cu — per-GPU runtime behind the C ABI (include/b200kv.h).
+//
+// Stands in for LMCacheEngine.store / .retrieve as driven by vLLM's adapter
+// (vllm/.../lmcache_integration/vllm_v1_adapter.py:1115-1123 store, :882-889 retrieve) and for
+// the NIXL peer channel (helm/templates/deployment-vllm-multi.yaml:296-324).
+//
+// Streams (all created on the engine's device):
+//   s_gather   store kernels          (lowest priority: shares SMs with decode)
+//   s_d2h      staging -> pinned pool (copy engine)
+//   s_h2d      pinned pool -> staging (copy engine)
+//   s_scatter  load / pull kernels    (highest priority: on the TTFT critical path)
+// The caller's compute stream only ever waits for a *kernel* (gather done / scatter done),
+// never for a PCIe transfer of a store.
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "b200kv.h"
+#include "b200kv_kernels.cuh"
+
+using namespace b200kv;
+
+namespace {
+
+thread_local char g_err[512] = {0};
+
+void set_err(const char* what, cudaError_t e, int line) {
+  std::snprintf(g_err, sizeof(g_err), "%s: %s (%s) at b200kv_engine.cu:%d", what,
+                cudaGetErrorName(e), cudaGetErrorString(e), line);
+}
+
+#define CU_TRY(expr)                          \
+  do {                                        \
+    cudaError_t _e = (expr);                  \
+    if (_e != cudaSuccess) {                  \
+      set_err(#expr, _e, __LINE__);           \
+      return B200KV_ENODEV;                   \
+    }                                         \
+  } while (0)
+
+constexpr int kTableSlots = 16;
+constexpr size_t kTableBytes = 1u << 20;
+constexpr int kMaxPeers = 64;
+constexpr uint32_t kStageMax = 32u << 10;
+
+struct StageSlot {
+  cudaEvent_t free_ev = nullptr;  // recorded when the last consumer of this slot is done
+  bool used = false;
+};
+
+struct TableSlot {
+  uint8_t* host = nullptr;  // pinned
+  uint8_t* dev = nullptr;
+  cudaEvent_t ev = nullptr;  // H2D of the table finished (host side reusable)
+  cudaEvent_t done_ev = nullptr;  // kernels reading the device table finished
+  bool used = false;
+};
+
+struct Op {
+  uint64_t id = 0;
+  b200kv_pool* pool = nullptr;
+  std::vector<uint64_t> commit_keys;   // store: commit after D2H
+  std::vector<uint64_t> release_keys;  // load: unpin after scatter
+  cudaEvent_t done = nullptr;
+  std::atomic<int> host_done{0};
+};
+
+void CUDART_CB op_host_cb(void* p) {
+  Op* op = static_cast<Op*>(p);
+  if (op->pool) {
+    for (uint64_t k : op->commit_keys) b200kv_pool_commit(op->pool, k);
+    for (uint64_t k : op->release_keys) b200kv_pool_release(op->pool, k);
+  }
+  op->host_done.store(1, std::memory_order_release);
+}
+
+struct Peer {
+  bool valid = false;
+  int device = -1;
+  uint64_t* d_bases = nullptr;
+  uint64_t block_stride = 0;
+  uint64_t n_blocks = 0;
+  std::vector<void*> opened;  // cudaIpcOpenMemHandle mappings to close
+};
+
+struct Geometry {
+  uint32_t L, H, D, elem, bs, C, planes;
+  uint32_t token_bytes;   // H*D*elem
+  uint64_t slab_bytes;    // C*token_bytes (RAW) or C*H*D (FP8)
+  uint64_t chunk_bytes;
+  uint64_t scales_off;    // FP8 only
+  uint32_t fmt_token_bytes;
+};
+
+int make_geometry(const b200kv_engine_config* c, Geometry* g) {
+  if (c->n_layers <= 0 || c->n_kv_heads <= 0 || c->head_dim <= 0 || c->block_tokens <= 0 ||
+      c->chunk_tokens <= 0 || c->chunk_tokens % c->block_tokens)
+    return B200KV_EINVAL;
+  if (c->elem_bytes != 1 && c->elem_bytes != 2 && c->elem_bytes != 4) return B200KV_EINVAL;
+  g->L = c->n_layers;
+  g->H = c->n_kv_heads;
+  g->D = c->head_dim;
+  g->elem = c->elem_bytes;
+  g->bs = c->block_tokens;
+  g->C = c->chunk_tokens;
+  g->planes = 2u * g->L;
+  g->token_bytes = g->H * g->D * g->elem;
+  if (g->token_bytes % 16) return B200KV_EINVAL;  // 16-byte vectors / bulk-copy granularity
+  if (c->format == B200KV_FMT_RAW) {
+    g->fmt_token_bytes = g->token_bytes;
+    g->slab_bytes = static_cast<uint64_t>(g->C) * g->token_bytes;
+    g->scales_off = 0;
+    g->chunk_bytes = g->slab_bytes * g->planes;
+  } else if (c->format == B200KV_FMT_FP8) {
+    if (g->elem != 2) return B200KV_ENOTSUP;  // source must be bf16
+    if (g->H > kMaxHeads) return B200KV_ENOTSUP;
+    if (g->C % kCluster) return B200KV_EINVAL;
+    if ((g->D * 2) % 16) return B200KV_EINVAL;
+    g->fmt_token_bytes = g->token_bytes / 2;
+    g->slab_bytes = static_cast<uint64_t>(g->C) * g->fmt_token_bytes;
+    g->scales_off = g->slab_bytes * g->planes;
+    g->chunk_bytes = g->scales_off + static_cast<uint64_t>(g->planes) * g->H * sizeof(float);
+    g->chunk_bytes = (g->chunk_bytes + 255) / 256 * 256;
+  } else {
+    return B200KV_EINVAL;
+  }
+  return B200KV_OK;
+}
+
+}  // namespace
+
+struct b200kv_ctx {
+  b200kv_engine_config cfg{};
+  Geometry g{};
+  b200kv_pool* pool = nullptr;
+  bool pool_registered = false;
+  void* pool_base = nullptr;
+  int sm_count = 148;
+  std::mutex mu;
+
+  cudaStream_t s_gather = nullptr, s_d2h = nullptr, s_h2d = nullptr, s_scatter = nullptr;
+  uint64_t* d_bases = nullptr;
+  bool kv_registered = false;
+  std::vector<const void*> h_k, h_v;
+
+  uint8_t* d_staging = nullptr;
+  std::vector<StageSlot> stage;
+  uint32_t stage_next = 0;
+
+  TableSlot tables[kTableSlots];
+  uint32_t table_next = 0;
+
+  Peer peers[kMaxPeers];
+
+  uint64_t next_ticket = 1;
+  std::map<uint64_t, std::unique_ptr<Op>> ops;
+
+  // timing of the most recent kernel batch of each kind (CUDA events on the launching stream)
+  struct Timing {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t used = 0;
+  } timing[3];
+
+  b200kv_engine_stats stats{};
+
+  // bulk-kernel launch shape
+  int S = 4, LAG = 2, ctas_per_sm = 1;
+  uint32_t piece_tokens = 0, pieces = 0, stage_bytes = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// ---- run construction (host) -----------------------------------------------------------------
+// slot_mapping[i] for op-relative token i (vllm_v1_adapter.py:368-375).  A run never crosses a
+// vLLM block or a chunk boundary, so both sides of every run are contiguous byte ranges.
+int build_runs(const b200kv_ctx* ctx, const int64_t* slots, int64_t tok_begin, int64_t tok_end,
+               int64_t b_shift, std::vector<Run>* runs) {
+  const Geometry& g = ctx->g;
+  const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
+  Run cur{0, 0, 0};
+  for (int64_t i = tok_begin; i < tok_end; ++i) {
+    const int64_t s = slots[i];
+    if (s < 0 || s >= max_slot) return B200KV_EINVAL;
+    const bool extend = cur.n > 0 && s == static_cast<int64_t>(cur.a) + cur.n && (s % g.bs) != 0 &&
+                        (i % g.C) != 0;
+    if (extend) {
+      ++cur.n;
+    } else {
+      if (cur.n) runs->push_back(cur);
+      cur.a = static_cast<int32_t>(s);
+      cur.b = static_cast<int32_t>(i - b_shift);
+      cur.n = 1;
+    }
+  }
+  if (cur.n) runs->push_back(cur);
+  return B200KV_OK;
+}
+
+int build_pull_runs(const b200kv_ctx* ctx, const Peer& peer, const int64_t* src, const int64_t* dst,
+                    int64_t n, std::vector<Run>* runs) {
+  const Geometry& g = ctx->g;
+  const int64_t max_dst = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
+  const int64_t max_src = static_cast<int64_t>(peer.n_blocks) * g.bs;
+  Run cur{0, 0, 0};
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t s = src[i], d = dst[i];
+    if (s < 0 || s >= max_src || d < 0 || d >= max_dst) return B200KV_EINVAL;
+    const bool extend = cur.n > 0 && s == static_cast<int64_t>(cur.a) + cur.n &&
+                        d == static_cast<int64_t>(cur.b) + cur.n && (s % g.bs) != 0 && (d % g.bs) != 0;
+    if (extend) {
+      ++cur.n;
+    } else {
+      if (cur.n) runs->push_back(cur);
+      cur.a = static_cast<int32_t>(s);
+      cur.b = static_cast<int32_t>(d);
+      cur.n = 1;
+    }
+  }
+  if (cur.n) runs->push_back(cur);
+  return B200KV_OK;
+}
+
+// ---- table ring ------------------------------------------------------------------------------
+struct TableView {
+  TableSlot* slot;
+  size_t runs_off, addrs_off, offs_off, bytes;
+};
+
+int table_acquire(b200kv_ctx* ctx, size_t n_runs, size_t n_chunks, TableView* tv) {
+  const size_t runs_bytes = (n_runs * sizeof(Run) + 15) / 16 * 16;
+  const size_t addrs_bytes = (n_chunks * 8 + 15) / 16 * 16;
+  const size_t offs_bytes = ((n_chunks + 1) * 4 + 15) / 16 * 16;
+  const size_t total = runs_bytes + addrs_bytes + offs_bytes;
+  if (total > kTableBytes) return B200KV_EINVAL;  // op too large: caller must split
+  TableSlot& t = ctx->tables[ctx->table_next];
+  ctx->table_next = (ctx->table_next + 1) % kTableSlots;
+  if (t.used) {  // host must not overwrite a table whose upload / readers are still in flight
+    CU_TRY(cudaEventSynchronize(t.ev));
+    CU_TRY(cudaEventSynchronize(t.done_ev));
+  }
+  tv->slot = &t;
+  tv->runs_off = 0;
+  tv->addrs_off = runs_bytes;
+  tv->offs_off = runs_bytes + addrs_bytes;
+  tv->bytes = total;
+  return B200KV_OK;
+}
+
+int table_upload(b200kv_ctx* ctx, const TableView& tv, cudaStream_t s) {
+  CU_TRY(cudaMemcpyAsync(tv.slot->dev, tv.slot->host, tv.bytes, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaEventRecord(tv.slot->ev, s));
+  tv.slot->used = true;
+  ctx->stats.h2d_bytes += tv.bytes;
+  return B200KV_OK;
+}
+
+// ---- timing events -----------------------------------------------------------------------------
+void timing_reset(b200kv_ctx* ctx, int which) { ctx->timing[which].used = 0; }
+
+int timing_begin(b200kv_ctx* ctx, int which, cudaStream_t s) {
+  auto& t = ctx->timing[which];
+  if (t.used == t.ev.size()) {
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a));
+    CU_TRY(cudaEventCreate(&b));
+    t.ev.emplace_back(a, b);
+  }
+  CU_TRY(cudaEventRecord(t.ev[t.used].first, s));
+  return B200KV_OK;
+}
+int timing_end(b200kv_ctx* ctx, int which, cudaStream_t s) {
+  auto& t = ctx->timing[which];
+  CU_TRY(cudaEventRecord(t.ev[t.used].second, s));
+  ++t.used;
+  return B200KV_OK;
+}
+
+// ---- kernel launches ---------------------------------------------------------------------------
+template <int MODE, int S, int LAG>
+int launch_bulk_t(b200kv_ctx* ctx, const CopyParams& p, cudaStream_t s) {
+  const size_t smem = 256 + static_cast<size_t>(S) * ctx->stage_bytes;
+  static bool attr_set[8] = {false};  // per device ordinal (<=8 GPUs per box)
+  const int dev = ctx->cfg.device & 7;
+  if (!attr_set[dev]) {
+    CU_TRY(cudaFuncSetAttribute(kv_bulk_copy_kernel<MODE, S, LAG>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev] = true;
+  }
+  uint32_t grid = static_cast<uint32_t>(ctx->sm_count * ctx->ctas_per_sm);
+  grid = std::min(grid, p.total_units);
+  if (grid == 0) return B200KV_OK;
+  kv_bulk_copy_kernel<MODE, S, LAG><<<grid, 32, smem, s>>>(p, ctx->stage_bytes);
+  CU_TRY(cudaGetLastError());
+  ++ctx->stats.n_kernel_launches;
+  return B200KV_OK;
+}
+
+template <int MODE>
+int launch_bulk(b200kv_ctx* ctx, const CopyParams& p, cudaStream_t s) {
+  switch (ctx->S * 10 + ctx->LAG) {
+    case 21: return launch_bulk_t<MODE, 2, 1>(ctx, p, s);
+    case 31: return launch_bulk_t<MODE, 3, 1>(ctx, p, s);
+    case 32: return launch_bulk_t<MODE, 3, 2>(ctx, p, s);
+    case 41: return launch_bulk_t<MODE, 4, 1>(ctx, p, s);
+    case 42: return launch_bulk_t<MODE, 4, 2>(ctx, p, s);
+    case 43: return launch_bulk_t<MODE, 4, 3>(ctx, p, s);
+    case 63: return launch_bulk_t<MODE, 6, 3>(ctx, p, s);
+    case 64: return launch_bulk_t<MODE, 6, 4>(ctx, p, s);
+    default: return B200KV_EINVAL;
+  }
+}
+
+template <int MODE>
+int launch_copy(b200kv_ctx* ctx, const CopyParams& p, cudaStream_t s) {
+  if (ctx->cfg.variant == B200KV_VARIANT_LDG) {
+    uint32_t grid = static_cast<uint32_t>(ctx->sm_count * 8);
+    grid = std::min(grid, p.total_units);
+    if (grid == 0) return B200KV_OK;
+    kv_ldg_copy_kernel<MODE><<<grid, 256, 0, s>>>(p);
+    CU_TRY(cudaGetLastError());
+    ++ctx->stats.n_kernel_launches;
+    return B200KV_OK;
+  }
+  return launch_bulk<MODE>(ctx, p, s);
+}
+
+PagedSide local_side(const b200kv_ctx* ctx) {
+  PagedSide s;
+  s.bases = ctx->d_bases;
+  s.block_stride = ctx->cfg.block_stride_bytes;
+  s.block_tokens = ctx->g.bs;
+  s.token_bytes = ctx->g.token_bytes;
+  return s;
+}
+
+CopyParams make_copy_params(const b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
+                            size_t run_begin, size_t n_runs) {
+  CopyParams p{};
+  p.paged = local_side(ctx);
+  p.peer = p.paged;
+  p.chunk.chunk_addrs = reinterpret_cast<const uint64_t*>(dev_table + tv.addrs_off);
+  p.chunk.slab_bytes = ctx->g.slab_bytes;
+  p.chunk.chunk_tokens = ctx->g.C;
+  p.chunk.token_bytes = ctx->g.fmt_token_bytes;
+  p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off) + run_begin;
+  p.n_runs = static_cast<uint32_t>(n_runs);
+  p.n_planes = ctx->g.planes;
+  p.pieces = ctx->pieces;
+  p.piece_tokens = ctx->piece_tokens;
+  p.total_units = p.n_runs * p.n_planes * p.pieces;
+  return p;
+}
+
+int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
+                     uint32_t n_chunks, uint32_t n_tokens, cudaStream_t s) {
+  Fp8StoreParams p{};
+  p.paged = local_side(ctx);
+  p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off);
+  p.chunk_run_off = reinterpret_cast<const uint32_t*>(dev_table + tv.offs_off);
+  p.chunk_addrs = reinterpret_cast<const uint64_t*>(dev_table + tv.addrs_off);
+  p.n_chunks = n_chunks;
+  p.n_planes = ctx->g.planes;
+  p.chunk_tokens = ctx->g.C;
+  p.n_tokens = n_tokens;
+  p.n_heads = ctx->g.H;
+  p.head_bytes = ctx->g.D * 2;
+  p.slab_q_bytes = ctx->g.slab_bytes;
+  p.scales_off = ctx->g.scales_off;
+  const size_t smem = static_cast<size_t>(ctx->g.C / kCluster) * ctx->g.token_bytes;
+  if (smem > 200 * 1024) return B200KV_ENOTSUP;
+  static bool attr_set[8] = {false};
+  const int dev = ctx->cfg.device & 7;
+  if (!attr_set[dev]) {
+    CU_TRY(cudaFuncSetAttribute(kv_fp8_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                200 * 1024));
+    attr_set[dev] = true;
+  }
+  const uint32_t grid = kCluster * n_chunks * ctx->g.planes;
+  if (grid == 0) return B200KV_OK;
+  kv_fp8_store_kernel<<<grid, kFp8Threads, smem, s>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++ctx->stats.n_kernel_launches;
+  return B200KV_OK;
+}
+
+int launch_fp8_load(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
+                    size_t run_begin, size_t n_runs, cudaStream_t s) {
+  Fp8LoadParams p{};
+  p.paged = local_side(ctx);
+  p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off) + run_begin;
+  p.chunk_addrs = reinterpret_cast<const uint64_t*>(dev_table + tv.addrs_off);
+  p.n_runs = static_cast<uint32_t>(n_runs);
+  p.n_planes = ctx->g.planes;
+  p.chunk_tokens = ctx->g.C;
+  p.n_heads = ctx->g.H;
+  p.head_bytes = ctx->g.D * 2;
+  p.slab_q_bytes = ctx->g.slab_bytes;
+  p.scales_off = ctx->g.scales_off;
+  p.total_units = p.n_runs * p.n_planes;
+  const size_t smem = static_cast<size_t>(ctx->g.bs) * ctx->g.fmt_token_bytes;
+  if (smem > 48 * 1024) return B200KV_ENOTSUP;
+  uint32_t grid = std::min<uint32_t>(p.total_units, static_cast<uint32_t>(ctx->sm_count) * 8u);
+  if (grid == 0) return B200KV_OK;
+  kv_fp8_load_kernel<<<grid, kFp8Threads, smem, s>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++ctx->stats.n_kernel_launches;
+  return B200KV_OK;
+}
+
+// chunk-side copy between staging and the pinned pool; partial chunks move only their tokens.
+int copy_chunk(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, cudaMemcpyKind kind,
+               cudaStream_t s) {
+  const Geometry& g = ctx->g;
+  uint64_t moved;
+  if (n_tok == g.C) {
+    CU_TRY(cudaMemcpyAsync(dst, src, g.chunk_bytes, kind, s));
+    moved = g.chunk_bytes;
+  } else {
+    const size_t width = static_cast<size_t>(n_tok) * g.fmt_token_bytes;
+    CU_TRY(cudaMemcpy2DAsync(dst, g.slab_bytes, src, g.slab_bytes, width, g.planes, kind, s));
+    moved = width * g.planes;
+    if (ctx->cfg.format == B200KV_FMT_FP8) {
+      const size_t sb = static_cast<size_t>(g.planes) * g.H * sizeof(float);
+      CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + g.scales_off,
+                             static_cast<const uint8_t*>(src) + g.scales_off, sb, kind, s));
+      moved += sb;
+    }
+  }
+  if (kind == cudaMemcpyDeviceToHost) ctx->stats.d2h_bytes += moved;
+  else ctx->stats.h2d_bytes += moved;
+  return B200KV_OK;
+}
+
+void reap(b200kv_ctx* ctx) {
+  for (auto it = ctx->ops.begin(); it != ctx->ops.end();) {
+    Op* op = it->second.get();
+    if (cudaEventQuery(op->done) == cudaSuccess && op->host_done.load(std::memory_order_acquire)) {
+      cudaEventDestroy(op->done);
+      it = ctx->ops.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int b200kv_abi_version(void) { return B200KV_ABI_VERSION; }
+
+extern "C" const char* b200kv_last_error(void) { return g_err; }
+
+extern "C" const char* b200kv_strerror(int err) {
+  switch (err) {
+    case B200KV_OK: return "ok";
+    case B200KV_EINVAL: return "invalid argument";
+    case B200KV_ENOMEM: return "out of memory";
+    case B200KV_ENODEV: return "CUDA device unavailable or CUDA call failed";
+    case B200KV_ENOENT: return "not found";
+    case B200KV_EEXIST: return "already exists";
+    case B200KV_ENOSPC: return "pool full";
+    case B200KV_ENOTSUP: return "not supported";
+    case B200KV_EBUSY: return "busy";
+    default: return std::strerror(-err);
+  }
+}
+
+extern "C" int64_t b200kv_engine_chunk_bytes(const b200kv_engine_config* cfg) {
+  if (!cfg) return B200KV_EINVAL;
+  Geometry g;
+  const int rc = make_geometry(cfg, &g);
+  if (rc) return rc;
+  return static_cast<int64_t>(g.chunk_bytes);
+}
+
+extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool* pool,
+                                    b200kv_ctx** out) {
+  if (!cfg || !out) return B200KV_EINVAL;
+  *out = nullptr;
+  Geometry g;
+  int rc = make_geometry(cfg, &g);
+  if (rc) return rc;
+  if (cfg->block_stride_bytes < static_cast<uint64_t>(g.bs) * g.token_bytes ||
+      cfg->block_stride_bytes % 16 || cfg->n_blocks == 0 ||
+      cfg->n_blocks * g.bs > 0x7fffffffull)
+    return B200KV_EINVAL;
+
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    std::snprintf(g_err, sizeof(g_err),
+                  "no CUDA device: libb200kv has no CPU fallback (the oracle/ directory is test "
+                  "infrastructure only)");
+    return B200KV_ENODEV;
+  }
+  if (cfg->device < 0 || cfg->device >= n_dev) return B200KV_EINVAL;
+  DeviceGuard dg(cfg->device);
+  if (!dg.ok) return B200KV_ENODEV;
+
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    std::snprintf(g_err, sizeof(g_err), "device %d is sm_%d%d; this library is built for sm_100a only",
+                  cfg->device, prop.major, prop.minor);
+    return B200KV_ENOTSUP;
+  }
+
+  std::unique_ptr<b200kv_ctx> ctx(new (std::nothrow) b200kv_ctx());
+  if (!ctx) return B200KV_ENOMEM;
+  ctx->cfg = *cfg;
+  ctx->g = g;
+  ctx->pool = pool;
+  ctx->sm_count = prop.multiProcessorCount;
+
+  // launch shape of the bulk kernel
+  ctx->S = cfg->stages > 0 ? cfg->stages : env_int("B200KV_STAGES", 4);
+  ctx->LAG = env_int("B200KV_LAG", ctx->S / 2);
+  ctx->ctas_per_sm = cfg->ctas_per_sm > 0 ? cfg->ctas_per_sm : env_int("B200KV_CTAS_PER_SM", 1);
+  const uint32_t stage_max = static_cast<uint32_t>(env_int("B200KV_STAGE_KB", 32)) << 10;
+  if (g.token_bytes > stage_max || stage_max > kStageMax * 2) return B200KV_ENOTSUP;
+  ctx->piece_tokens = std::min<uint32_t>(g.bs, stage_max / g.token_bytes);
+  ctx->pieces = (g.bs + ctx->piece_tokens - 1) / ctx->piece_tokens;
+  ctx->stage_bytes = ctx->piece_tokens * g.token_bytes;
+  if (256 + static_cast<size_t>(ctx->S) * ctx->stage_bytes > 227u * 1024) return B200KV_EINVAL;
+
+  int lo_pri = 0, hi_pri = 0;
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+  CU_TRY(cudaStreamCreateWithPriority(&ctx->s_gather, cudaStreamNonBlocking, lo_pri));
+  CU_TRY(cudaStreamCreateWithPriority(&ctx->s_d2h, cudaStreamNonBlocking, lo_pri));
+  CU_TRY(cudaStreamCreateWithPriority(&ctx->s_h2d, cudaStreamNonBlocking, hi_pri));
+  CU_TRY(cudaStreamCreateWithPriority(&ctx->s_scatter, cudaStreamNonBlocking, hi_pri));
+
+  CU_TRY(cudaMalloc(&ctx->d_bases, sizeof(uint64_t) * g.planes));
+
+  const uint64_t n_stage = cfg->staging_bytes / g.chunk_bytes;
+  if (n_stage > 0) {
+    CU_TRY(cudaMalloc(&ctx->d_staging, n_stage * g.chunk_bytes));
+    ctx->stage.resize(n_stage);
+    for (auto& s : ctx->stage) CU_TRY(cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+  } else if (pool) {
+    return B200KV_EINVAL;  // store/load need at least one staging chunk
+  }
+  for (auto& t : ctx->tables) {
+    CU_TRY(cudaHostAlloc(&t.host, kTableBytes, cudaHostAllocDefault));
+    CU_TRY(cudaMalloc(&t.dev, kTableBytes));
+    CU_TRY(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&t.done_ev, cudaEventDisableTiming));
+  }
+
+  if (pool) {
+    void* base = nullptr;
+    uint64_t bytes = 0;
+    rc = b200kv_pool_region(pool, &base, &bytes);
+    if (rc) return rc;
+    b200kv_pool_stats ps;
+    b200kv_pool_get_stats(pool, &ps);
+    if (ps.slot_bytes < g.chunk_bytes) return B200KV_EINVAL;
+    // Pin the (possibly shared) pool for this process so D2H/H2D run at full PCIe speed and
+    // asynchronously.  Portable: every replica on the box registers the same segment.
+    CU_TRY(cudaHostRegister(base, bytes, cudaHostRegisterPortable));
+    ctx->pool_registered = true;
+    ctx->pool_base = base;
+  }
+  *out = ctx.release();
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_wait_all(b200kv_ctx* ctx);
+
+extern "C" int b200kv_engine_destroy(b200kv_ctx* ctx) {
+  if (!ctx) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  b200kv_wait_all(ctx);
+  cudaDeviceSynchronize();
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    reap(ctx);
+    for (auto& kv : ctx->ops) cudaEventDestroy(kv.second->done);
+    ctx->ops.clear();
+  }
+  if (ctx->pool_registered) cudaHostUnregister(ctx->pool_base);
+  for (auto& p : ctx->peers) {
+    if (!p.valid) continue;
+    for (void* m : p.opened) cudaIpcCloseMemHandle(m);
+    cudaFree(p.d_bases);
+  }
+  for (auto& t : ctx->tables) {
+    if (t.host) cudaFreeHost(t.host);
+    if (t.dev) cudaFree(t.dev);
+    if (t.ev) cudaEventDestroy(t.ev);
+    if (t.done_ev) cudaEventDestroy(t.done_ev);
+  }
+  for (auto& s : ctx->stage)
+    if (s.free_ev) cudaEventDestroy(s.free_ev);
+  for (auto& t : ctx->timing)
+    for (auto& e : t.ev) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+  if (ctx->d_staging) cudaFree(ctx->d_staging);
+  if (ctx->d_bases) cudaFree(ctx->d_bases);
+  for (cudaStream_t s : {ctx->s_gather, ctx->s_d2h, ctx->s_h2d, ctx->s_scatter})
+    if (s) cudaStreamDestroy(s);
+  delete ctx;
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_register_kv(b200kv_ctx* ctx, const void* const* k_ptrs,
+                                  const void* const* v_ptrs) {
+  if (!ctx || !k_ptrs || !v_ptrs) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::vector<uint64_t> h(ctx->g.planes);
+  ctx->h_k.assign(k_ptrs, k_ptrs + ctx->g.L);
+  ctx->h_v.assign(v_ptrs, v_ptrs + ctx->g.L);
+  for (uint32_t l = 0; l < ctx->g.L; ++l) {
+    const uint64_t k = reinterpret_cast<uint64_t>(k_ptrs[l]);
+    const uint64_t v = reinterpret_cast<uint64_t>(v_ptrs[l]);
+    if (!k || !v || (k % 16) || (v % 16)) return B200KV_EINVAL;
+    h[2 * l] = k;
+    h[2 * l + 1] = v;
+  }
+  CU_TRY(cudaMemcpy(ctx->d_bases, h.data(), sizeof(uint64_t) * h.size(), cudaMemcpyHostToDevice));
+  ctx->kv_registered = true;
+  return B200KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident gather / scatter
+// ------------------------------------------------------------------------------------------------
+static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_tokens, void* dev_chunks,
+                          void* stream, bool is_gather) {
+  if (!ctx || !slots || n_tokens <= 0 || !dev_chunks) return B200KV_EINVAL;
+  if (!ctx->kv_registered) return B200KV_EINVAL;
+  if (reinterpret_cast<uint64_t>(dev_chunks) % 16) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const Geometry& g = ctx->g;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint32_t n_chunks = static_cast<uint32_t>((n_tokens + g.C - 1) / g.C);
+
+  std::vector<Run> runs;
+  int rc = build_runs(ctx, slots, 0, n_tokens, 0, &runs);
+  if (rc) return rc;
+  TableView tv;
+  rc = table_acquire(ctx, runs.size(), n_chunks, &tv);
+  if (rc) return rc;
+  std::memcpy(tv.slot->host + tv.runs_off, runs.data(), runs.size() * sizeof(Run));
+  uint64_t* addrs = reinterpret_cast<uint64_t*>(tv.slot->host + tv.addrs_off);
+  uint32_t* offs = reinterpret_cast<uint32_t*>(tv.slot->host + tv.offs_off);
+  size_t r = 0;
+  for (uint32_t c = 0; c < n_chunks; ++c) {
+    addrs[c] = reinterpret_cast<uint64_t>(dev_chunks) + static_cast<uint64_t>(c) * g.chunk_bytes;
+    offs[c] = static_cast<uint32_t>(r);
+    while (r < runs.size() && static_cast<uint32_t>(runs[r].b) / g.C == c) ++r;
+  }
+  offs[n_chunks] = static_cast<uint32_t>(r);
+  rc = table_upload(ctx, tv, s);
+  if (rc) return rc;
+
+  const int which = is_gather ? 0 : 1;
+  timing_reset(ctx, which);
+  rc = timing_begin(ctx, which, s);
+  if (rc) return rc;
+  if (ctx->cfg.format == B200KV_FMT_FP8) {
+    rc = is_gather ? launch_fp8_store(ctx, tv.slot->dev, tv, n_chunks, static_cast<uint32_t>(n_tokens), s)
+                   : launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), s);
+  } else {
+    const CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, 0, runs.size());
+    rc = is_gather ? launch_copy<kStore>(ctx, p, s) : launch_copy<kLoad>(ctx, p, s);
+  }
+  if (rc) return rc;
+  rc = timing_end(ctx, which, s);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord(tv.slot->done_ev, s));
+  if (is_gather) ctx->stats.n_stored_tokens += n_tokens; else ctx->stats.n_loaded_tokens += n_tokens;
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_gather(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                             void* dev_chunks, void* stream) {
+  return gather_scatter(ctx, slot_mapping, n_tokens, dev_chunks, stream, true);
+}
+
+extern "C" int b200kv_scatter(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                              const void* dev_chunks, void* stream) {
+  return gather_scatter(ctx, slot_mapping, n_tokens, const_cast<void*>(dev_chunks), stream, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// store: paged HBM -> staging (kernel) -> pinned pool (DMA)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
+                                  const int64_t* slot_mapping, int64_t n_tokens,
+                                  void* compute_stream, uint64_t* ticket) {
+  if (!ctx || !keys || !slot_mapping || n_tokens <= 0 || !ticket) return B200KV_EINVAL;
+  if (!ctx->pool || !ctx->kv_registered || ctx->stage.empty()) return B200KV_EINVAL;
+  const Geometry& g = ctx->g;
+  if (n_chunks != static_cast<int32_t>((n_tokens + g.C - 1) / g.C)) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  reap(ctx);
+  cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
+  *ticket = 0;
+
+  // 1. reserve pool slots; chunks already present (or not placeable) are skipped
+  struct Todo { int32_t c; uint32_t slot; uint32_t n_tok; };
+  std::vector<Todo> todo;
+  for (int32_t c = 0; c < n_chunks; ++c) {
+    const uint32_t n_tok = static_cast<uint32_t>(std::min<int64_t>(g.C, n_tokens - static_cast<int64_t>(c) * g.C));
+    uint32_t slot = 0;
+    const int rc = b200kv_pool_reserve(ctx->pool, keys[c], static_cast<int32_t>(n_tok),
+                                       static_cast<uint32_t>(ctx->cfg.format), ctx->cfg.owner, &slot);
+    if (rc == B200KV_OK) todo.push_back({c, slot, n_tok});
+    else if (rc != B200KV_EEXIST && rc != B200KV_ENOSPC) return rc;
+  }
+  ++ctx->stats.n_store_ops;
+  if (todo.empty()) return B200KV_OK;
+
+  std::unique_ptr<Op> op(new Op());
+  op->id = ctx->next_ticket++;
+  op->pool = ctx->pool;
+  CU_TRY(cudaEventCreateWithFlags(&op->done, cudaEventDisableTiming));
+
+  cudaEvent_t ev_compute;
+  CU_TRY(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(ev_compute, cs));
+  CU_TRY(cudaStreamWaitEvent(ctx->s_gather, ev_compute, 0));
+  CU_TRY(cudaEventDestroy(ev_compute));
+
+  timing_reset(ctx, 0);
+  const size_t n_stage = ctx->stage.size();
+  for (size_t b0 = 0; b0 < todo.size(); b0 += n_stage) {
+    const size_t nb = std::min(n_stage, todo.size() - b0);
+    std::vector<Run> runs;
+    std::vector<uint32_t> offs(nb + 1);
+    std::vector<uint64_t> addrs(nb);
+    std::vector<uint32_t> sidx(nb);
+    uint32_t batch_tokens = 0;
+    for (size_t i = 0; i < nb; ++i) {
+      const Todo& t = todo[b0 + i];
+      offs[i] = static_cast<uint32_t>(runs.size());
+      const int64_t tb = static_cast<int64_t>(t.c) * g.C;
+      // dense op-relative token index: chunk i of this batch starts at i*C
+      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs);
+      if (rc) return rc;
+      sidx[i] = ctx->stage_next;
+      ctx->stage_next = (ctx->stage_next + 1) % static_cast<uint32_t>(n_stage);
+      addrs[i] = reinterpret_cast<uint64_t>(ctx->d_staging) + static_cast<uint64_t>(sidx[i]) * g.chunk_bytes;
+      if (ctx->stage[sidx[i]].used) CU_TRY(cudaStreamWaitEvent(ctx->s_gather, ctx->stage[sidx[i]].free_ev, 0));
+      batch_tokens = static_cast<uint32_t>(i) * g.C + t.n_tok;
+    }
+    offs[nb] = static_cast<uint32_t>(runs.size());
+    TableView tv;
+    int rc = table_acquire(ctx, runs.size(), nb, &tv);
+    if (rc) return rc;
+    std::memcpy(tv.slot->host + tv.runs_off, runs.data(), runs.size() * sizeof(Run));
+    std::memcpy(tv.slot->host + tv.addrs_off, addrs.data(), nb * 8);
+    std::memcpy(tv.slot->host + tv.offs_off, offs.data(), (nb + 1) * 4);
+    rc = table_upload(ctx, tv, ctx->s_gather);
+    if (rc) return rc;
+
+    rc = timing_begin(ctx, 0, ctx->s_gather);
+    if (rc) return rc;
+    if (ctx->cfg.format == B200KV_FMT_FP8) {
+      // a partial chunk is always the last of the op, hence the last of its batch
+      rc = launch_fp8_store(ctx, tv.slot->dev, tv, static_cast<uint32_t>(nb), batch_tokens, ctx->s_gather);
+    } else {
+      const CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, 0, runs.size());
+      rc = launch_copy<kStore>(ctx, p, ctx->s_gather);
+    }
+    if (rc) return rc;
+    rc = timing_end(ctx, 0, ctx->s_gather);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(tv.slot->done_ev, ctx->s_gather));
+    // the pages may be reused as soon as the gather is done: compute waits for the kernel only
+    CU_TRY(cudaStreamWaitEvent(cs, tv.slot->done_ev, 0));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, tv.slot->done_ev, 0));
+    for (size_t i = 0; i < nb; ++i) {
+      const Todo& t = todo[b0 + i];
+      rc = copy_chunk(ctx, b200kv_pool_slot_ptr(ctx->pool, t.slot), reinterpret_cast<void*>(addrs[i]),
+                      t.n_tok, cudaMemcpyDeviceToHost, ctx->s_d2h);
+      if (rc) return rc;
+      CU_TRY(cudaEventRecord(ctx->stage[sidx[i]].free_ev, ctx->s_d2h));
+      ctx->stage[sidx[i]].used = true;
+      op->commit_keys.push_back(keys[t.c]);
+      ctx->stats.n_stored_tokens += t.n_tok;
+    }
+  }
+  CU_TRY(cudaLaunchHostFunc(ctx->s_d2h, op_host_cb, op.get()));
+  CU_TRY(cudaEventRecord(op->done, ctx->s_d2h));
+  *ticket = op->id;
+  ctx->ops.emplace(op->id, std::move(op));
+  return B200KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// load: pinned pool -> staging (DMA) -> paged HBM (kernel), pipelined per chunk
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
+                                 const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
+                                 void* compute_stream, uint64_t* ticket, int64_t* n_loaded_tokens) {
+  if (!ctx || !keys || !slot_mapping || n_tokens <= 0 || !ticket || skip_chunks < 0)
+    return B200KV_EINVAL;
+  if (!ctx->pool || !ctx->kv_registered || ctx->stage.empty()) return B200KV_EINVAL;
+  const Geometry& g = ctx->g;
+  if (n_chunks != static_cast<int32_t>((n_tokens + g.C - 1) / g.C)) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  reap(ctx);
+  cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
+  *ticket = 0;
+  if (n_loaded_tokens) *n_loaded_tokens = 0;
+
+  struct Todo { int32_t c; uint32_t slot; uint32_t n_tok; };
+  std::vector<Todo> todo;
+  for (int32_t c = skip_chunks; c < n_chunks; ++c) {
+    const uint32_t want = static_cast<uint32_t>(std::min<int64_t>(g.C, n_tokens - static_cast<int64_t>(c) * g.C));
+    uint32_t slot = 0, fmt = 0;
+    int32_t have = 0;
+    if (b200kv_pool_acquire(ctx->pool, keys[c], &slot, &have, &fmt) != B200KV_OK) break;
+    if (static_cast<uint32_t>(have) != want || fmt != static_cast<uint32_t>(ctx->cfg.format)) {
+      b200kv_pool_release(ctx->pool, keys[c]);
+      break;
+    }
+    todo.push_back({c, slot, want});
+  }
+  ++ctx->stats.n_load_ops;
+  if (todo.empty()) return B200KV_OK;
+
+  std::unique_ptr<Op> op(new Op());
+  op->id = ctx->next_ticket++;
+  op->pool = ctx->pool;
+  for (const Todo& t : todo) op->release_keys.push_back(keys[t.c]);
+  // From here on every exit path must run the release callback; errors below are CUDA failures
+  // (fatal for the engine), so the pins are dropped by the caller destroying the engine.
+  CU_TRY(cudaEventCreateWithFlags(&op->done, cudaEventDisableTiming));
+
+  cudaEvent_t ev_compute;
+  CU_TRY(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(ev_compute, cs));
+  CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, ev_compute, 0));
+  CU_TRY(cudaEventDestroy(ev_compute));
+
+  timing_reset(ctx, 1);
+  const size_t n_stage = ctx->stage.size();
+  int64_t loaded = 0;
+  for (size_t b0 = 0; b0 < todo.size(); b0 += n_stage) {
+    const size_t nb = std::min(n_stage, todo.size() - b0);
+    std::vector<Run> runs;
+    std::vector<uint32_t> offs(nb + 1);
+    std::vector<uint64_t> addrs(nb);
+    std::vector<uint32_t> sidx(nb);
+    for (size_t i = 0; i < nb; ++i) {
+      const Todo& t = todo[b0 + i];
+      offs[i] = static_cast<uint32_t>(runs.size());
+      const int64_t tb = static_cast<int64_t>(t.c) * g.C;
+      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs);
+      if (rc) return rc;
+      sidx[i] = ctx->stage_next;
+      ctx->stage_next = (ctx->stage_next + 1) % static_cast<uint32_t>(n_stage);
+      addrs[i] = reinterpret_cast<uint64_t>(ctx->d_staging) + static_cast<uint64_t>(sidx[i]) * g.chunk_bytes;
+    }
+    offs[nb] = static_cast<uint32_t>(runs.size());
+    TableView tv;
+    int rc = table_acquire(ctx, runs.size(), nb, &tv);
+    if (rc) return rc;
+    std::memcpy(tv.slot->host + tv.runs_off, runs.data(), runs.size() * sizeof(Run));
+    std::memcpy(tv.slot->host + tv.addrs_off, addrs.data(), nb * 8);
+    std::memcpy(tv.slot->host + tv.offs_off, offs.data(), (nb + 1) * 4);
+    rc = table_upload(ctx, tv, ctx->s_scatter);
+    if (rc) return rc;
+
+    for (size_t i = 0; i < nb; ++i) {
+      const Todo& t = todo[b0 + i];
+      StageSlot& ss = ctx->stage[sidx[i]];
+      if (ss.used) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, ss.free_ev, 0));
+      rc = copy_chunk(ctx, reinterpret_cast<void*>(addrs[i]), b200kv_pool_slot_ptr(ctx->pool, t.slot),
+                      t.n_tok, cudaMemcpyHostToDevice, ctx->s_h2d);
+      if (rc) return rc;
+      CU_TRY(cudaEventRecord(ss.free_ev, ctx->s_h2d));  // reused as "chunk landed" first ...
+      CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, ss.free_ev, 0));
+      rc = timing_begin(ctx, 1, ctx->s_scatter);
+      if (rc) return rc;
+      const size_t r0 = offs[i], rn = offs[i + 1] - offs[i];
+      if (ctx->cfg.format == B200KV_FMT_FP8) {
+        rc = launch_fp8_load(ctx, tv.slot->dev, tv, r0, rn, ctx->s_scatter);
+      } else {
+        const CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, r0, rn);
+        rc = launch_copy<kLoad>(ctx, p, ctx->s_scatter);
+      }
+      if (rc) return rc;
+      rc = timing_end(ctx, 1, ctx->s_scatter);
+      if (rc) return rc;
+      CU_TRY(cudaEventRecord(ss.free_ev, ctx->s_scatter));  // ... then as "slot drained"
+      ss.used = true;
+      loaded += t.n_tok;
+    }
+    CU_TRY(cudaEventRecord(tv.slot->done_ev, ctx->s_scatter));
+  }
+  CU_TRY(cudaLaunchHostFunc(ctx->s_scatter, op_host_cb, op.get()));
+  CU_TRY(cudaEventRecord(op->done, ctx->s_scatter));
+  CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));  // the forward pass must see the loaded pages
+  ctx->stats.n_loaded_tokens += loaded;
+  if (n_loaded_tokens) *n_loaded_tokens = loaded;
+  *ticket = op->id;
+  ctx->ops.emplace(op->id, std::move(op));
+  return B200KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tickets
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200kv_poll(b200kv_ctx* ctx, uint64_t ticket, int* done) {
+  if (!ctx || !done) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ticket == 0) { *done = 1; return B200KV_OK; }
+  auto it = ctx->ops.find(ticket);
+  if (it == ctx->ops.end()) { *done = 1; return B200KV_OK; }  // already reaped
+  Op* op = it->second.get();
+  const cudaError_t q = cudaEventQuery(op->done);
+  if (q == cudaSuccess && op->host_done.load(std::memory_order_acquire)) {
+    cudaEventDestroy(op->done);
+    ctx->ops.erase(it);
+    *done = 1;
+  } else if (q == cudaSuccess || q == cudaErrorNotReady) {
+    *done = 0;
+  } else {
+    set_err("cudaEventQuery", q, __LINE__);
+    return B200KV_ENODEV;
+  }
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_wait(b200kv_ctx* ctx, uint64_t ticket) {
+  if (!ctx) return B200KV_EINVAL;
+  if (ticket == 0) return B200KV_OK;
+  DeviceGuard dg(ctx->cfg.device);
+  cudaEvent_t ev = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->ops.find(ticket);
+    if (it == ctx->ops.end()) return B200KV_OK;
+    ev = it->second->done;
+  }
+  CU_TRY(cudaEventSynchronize(ev));
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->ops.find(ticket);
+  if (it != ctx->ops.end()) {
+    while (!it->second->host_done.load(std::memory_order_acquire)) { /* callback precedes event */ }
+    cudaEventDestroy(it->second->done);
+    ctx->ops.erase(it);
+  }
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_wait_all(b200kv_ctx* ctx) {
+  if (!ctx) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  for (cudaStream_t s : {ctx->s_gather, ctx->s_d2h, ctx->s_h2d, ctx->s_scatter})
+    if (s) CU_TRY(cudaStreamSynchronize(s));
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  reap(ctx);
+  return B200KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peers
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200kv_export_ipc(b200kv_ctx* ctx, b200kv_ipc_desc* descs_out, int32_t n_descs) {
+  if (!ctx || !descs_out) return B200KV_EINVAL;
+  if (!ctx->kv_registered || n_descs != static_cast<int32_t>(ctx->g.planes)) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  typedef CUresult (*GetRange)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  CU_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+  if (!fn || qr != cudaDriverEntryPointSuccess) return B200KV_ENODEV;
+  GetRange get_range = reinterpret_cast<GetRange>(fn);
+  for (uint32_t l = 0; l < ctx->g.L; ++l) {
+    for (int kv = 0; kv < 2; ++kv) {
+      const void* p = kv ? ctx->h_v[l] : ctx->h_k[l];
+      CUdeviceptr base = 0;
+      size_t size = 0;
+      if (get_range(&base, &size, reinterpret_cast<CUdeviceptr>(p)) != CUDA_SUCCESS) return B200KV_ENODEV;
+      b200kv_ipc_desc& d = descs_out[kv * ctx->g.L + l];  // K planes then V planes
+      std::memset(&d, 0, sizeof(d));
+      cudaIpcMemHandle_t h;
+      CU_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+      static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+      std::memcpy(d.handle, &h, 64);
+      d.offset = reinterpret_cast<uint64_t>(p) - static_cast<uint64_t>(base);
+      d.alloc_bytes = size;
+    }
+  }
+  return B200KV_OK;
+}
+
+static int install_peer(b200kv_ctx* ctx, int32_t peer_id, int32_t peer_device,
+                        const std::vector<uint64_t>& bases, uint64_t stride, uint64_t n_blocks,
+                        std::vector<void*>&& opened) {
+  Peer& p = ctx->peers[peer_id];
+  if (p.valid) return B200KV_EEXIST;
+  CU_TRY(cudaMalloc(&p.d_bases, sizeof(uint64_t) * bases.size()));
+  CU_TRY(cudaMemcpy(p.d_bases, bases.data(), sizeof(uint64_t) * bases.size(), cudaMemcpyHostToDevice));
+  p.device = peer_device;
+  p.block_stride = stride;
+  p.n_blocks = n_blocks;
+  p.opened = std::move(opened);
+  p.valid = true;
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_import_peer(b200kv_ctx* ctx, int32_t peer_id, int32_t peer_device,
+                                  const b200kv_ipc_desc* descs, int32_t n_descs,
+                                  uint64_t peer_block_stride_bytes, uint64_t peer_n_blocks) {
+  if (!ctx || !descs || peer_id < 0 || peer_id >= kMaxPeers) return B200KV_EINVAL;
+  if (n_descs != static_cast<int32_t>(ctx->g.planes) || peer_n_blocks == 0 ||
+      peer_n_blocks * ctx->g.bs > 0x7fffffffull)
+    return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  // one cudaIpcOpenMemHandle per distinct allocation
+  std::vector<std::pair<std::string, void*>> seen;
+  std::vector<void*> opened;
+  std::vector<uint64_t> bases(ctx->g.planes);
+  for (uint32_t l = 0; l < ctx->g.L; ++l) {
+    for (int kv = 0; kv < 2; ++kv) {
+      const b200kv_ipc_desc& d = descs[kv * ctx->g.L + l];
+      const std::string key(reinterpret_cast<const char*>(d.handle), 64);
+      void* base = nullptr;
+      for (auto& s : seen)
+        if (s.first == key) base = s.second;
+      if (!base) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, d.handle, 64);
+        CU_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        seen.emplace_back(key, base);
+        opened.push_back(base);
+      }
+      bases[2 * l + kv] = reinterpret_cast<uint64_t>(base) + d.offset;
+    }
+  }
+  return install_peer(ctx, peer_id, peer_device, bases, peer_block_stride_bytes, peer_n_blocks,
+                      std::move(opened));
+}
+
+extern "C" int b200kv_import_peer_ptrs(b200kv_ctx* ctx, int32_t peer_id, int32_t peer_device,
+                                       const void* const* k_ptrs, const void* const* v_ptrs,
+                                       uint64_t peer_block_stride_bytes, uint64_t peer_n_blocks) {
+  if (!ctx || !k_ptrs || !v_ptrs || peer_id < 0 || peer_id >= kMaxPeers) return B200KV_EINVAL;
+  if (peer_n_blocks == 0 || peer_n_blocks * ctx->g.bs > 0x7fffffffull) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (peer_device != ctx->cfg.device) {
+    int can = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&can, ctx->cfg.device, peer_device));
+    if (!can) return B200KV_ENOTSUP;
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+      set_err("cudaDeviceEnablePeerAccess", e, __LINE__);
+      return B200KV_ENODEV;
+    }
+    cudaGetLastError();
+  }
+  std::vector<uint64_t> bases(ctx->g.planes);
+  for (uint32_t l = 0; l < ctx->g.L; ++l) {
+    bases[2 * l] = reinterpret_cast<uint64_t>(k_ptrs[l]);
+    bases[2 * l + 1] = reinterpret_cast<uint64_t>(v_ptrs[l]);
+    if (!bases[2 * l] || !bases[2 * l + 1] || bases[2 * l] % 16 || bases[2 * l + 1] % 16)
+      return B200KV_EINVAL;
+  }
+  return install_peer(ctx, peer_id, peer_device, bases, peer_block_stride_bytes, peer_n_blocks, {});
+}
+
+extern "C" int b200kv_peer_pull_async(b200kv_ctx* ctx, int32_t peer_id, const int64_t* src_slots,
+                                      const int64_t* dst_slots, int64_t n_tokens,
+                                      void* compute_stream, uint64_t* ticket) {
+  if (!ctx || !src_slots || !dst_slots || n_tokens <= 0 || !ticket) return B200KV_EINVAL;
+  if (peer_id < 0 || peer_id >= kMaxPeers || !ctx->peers[peer_id].valid) return B200KV_ENOENT;
+  if (!ctx->kv_registered) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  reap(ctx);
+  const Peer& peer = ctx->peers[peer_id];
+  cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
+  *ticket = 0;
+
+  std::vector<Run> runs;
+  int rc = build_pull_runs(ctx, peer, src_slots, dst_slots, n_tokens, &runs);
+  if (rc) return rc;
+  TableView tv;
+  rc = table_acquire(ctx, runs.size(), 1, &tv);
+  if (rc) return rc;
+  std::memcpy(tv.slot->host + tv.runs_off, runs.data(), runs.size() * sizeof(Run));
+
+  std::unique_ptr<Op> op(new Op());
+  op->id = ctx->next_ticket++;
+  CU_TRY(cudaEventCreateWithFlags(&op->done, cudaEventDisableTiming));
+  cudaEvent_t ev_compute;
+  CU_TRY(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(ev_compute, cs));
+  CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, ev_compute, 0));
+  CU_TRY(cudaEventDestroy(ev_compute));
+  rc = table_upload(ctx, tv, ctx->s_scatter);
+  if (rc) return rc;
+
+  CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, 0, runs.size());
+  p.peer.bases = peer.d_bases;
+  p.peer.block_stride = peer.block_stride;
+  timing_reset(ctx, 2);
+  rc = timing_begin(ctx, 2, ctx->s_scatter);
+  if (rc) return rc;
+  rc = launch_copy<kPull>(ctx, p, ctx->s_scatter);
+  if (rc) return rc;
+  rc = timing_end(ctx, 2, ctx->s_scatter);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord(tv.slot->done_ev, ctx->s_scatter));
+  CU_TRY(cudaLaunchHostFunc(ctx->s_scatter, op_host_cb, op.get()));
+  CU_TRY(cudaEventRecord(op->done, ctx->s_scatter));
+  CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));
+  ++ctx->stats.n_pull_ops;
+  ctx->stats.n_pulled_tokens += n_tokens;
+  ctx->stats.p2p_bytes += static_cast<uint64_t>(n_tokens) * ctx->g.token_bytes * ctx->g.planes;
+  *ticket = op->id;
+  ctx->ops.emplace(op->id, std::move(op));
+  return B200KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stats
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200kv_engine_get_stats(b200kv_ctx* ctx, b200kv_engine_stats* out) {
+  if (!ctx || !out) return B200KV_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = ctx->stats;
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_last_kernel_ms(b200kv_ctx* ctx, int which, float* ms_out) {
+  if (!ctx || !ms_out || which < 0 || which > 2) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  float total = 0.f;
+  auto& t = ctx->timing[which];
+  for (size_t i = 0; i < t.used; ++i) {
+    float ms = 0.f;
+    CU_TRY(cudaEventSynchronize(t.ev[i].second));
+    CU_TRY(cudaEventElapsedTime(&ms, t.ev[i].first, t.ev[i].second));
+    total += ms;
+  }
+  *ms_out = total;
+  return B200KV_OK;
+}

@@ -1,0 +1,488 @@
+// b200kv_kernels.cuh — sm_100a kernels of the KV offload / transfer hot path.
+//
+// What they replace: LMCache's paged-memory GPU connector (`VLLMPagedMemGPUConnectorV2`,
+// named at vllm/.../lmcache_integration/vllm_v1_adapter.py:19-23,533-541) — an element-wise
+// gather/scatter between vLLM's paged KV cache and a contiguous (L,2,C,H,D) chunk — plus the
+// UCX/NIXL peer copy the reference configures for disaggregated prefill
+// (helm/templates/deployment-vllm-multi.yaml:296-324).
+//
+// All of them are HBM-bound byte movers: no tensor cores.  The design rules
+// that matter are coalescing, enough bytes in flight per SM to cover DRAM latency, and a grid
+// that is a multiple of the 148 SMs.
+//
+//   kv_bulk_copy_kernel  RAW store / load / peer pull.  One elected thread per CTA drives the
+//                        TMA engine: cp.async.bulk global->smem (mbarrier complete_tx) into an
+//                        S-stage ring, then cp.async.bulk smem->global (bulk_group).  No
+//                        registers touch the payload.  Persistent grid.
+//   kv_ldg_copy_kernel   same contract with 128-bit ld.global.nc / st.global (A/B variant).
+//   kv_fp8_store_kernel  cluster of 8 CTAs per (chunk, layer, K/V) slab: bulk-load 32 tokens
+//                        each into smem, per-head absmax in registers -> smem -> DSMEM exchange
+//                        across the cluster, quantise to e4m3 from smem, coalesced store.  HBM
+//                        is read exactly once.
+//   kv_fp8_load_kernel   bulk-load e4m3 piece -> dequantise -> 16-byte stores into the pages.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200kv {
+
+// One run = consecutive tokens that stay inside one vLLM block and one chunk.
+//   store / load : a = paged slot (block*bs + off) ; b = op-relative token index
+//   peer pull    : a = peer slot                   ; b = local slot
+struct Run {
+  int32_t a;
+  int32_t b;
+  int32_t n;
+};
+
+struct PagedSide {
+  const uint64_t* bases;  // device array [2*L]: K plane of layer l at [2l], V plane at [2l+1]
+  uint64_t block_stride;  // bytes between consecutive blocks of one plane
+  uint32_t block_tokens;
+  uint32_t token_bytes;   // H*D*elem (NHD: one token's heads are contiguous)
+};
+
+struct ChunkSide {
+  const uint64_t* chunk_addrs;  // device array [n_chunks]: where chunk c of this op lives
+  uint64_t slab_bytes;          // C * token_bytes(format): one (layer, K/V) slab
+  uint32_t chunk_tokens;
+  uint32_t token_bytes;         // bytes per token per slab in this format (RAW: 2048, FP8: 1024)
+};
+
+struct CopyParams {
+  PagedSide paged;        // local pages (store src / load dst / pull dst)
+  PagedSide peer;         // pull src (peer mapping); unused otherwise
+  ChunkSide chunk;
+  const Run* runs;
+  uint32_t n_runs;
+  uint32_t n_planes;      // 2*L
+  uint32_t pieces;        // pieces per run = ceil(block_tokens / piece_tokens)
+  uint32_t piece_tokens;  // tokens per piece (piece bytes <= stage bytes)
+  uint32_t total_units;   // n_runs * n_planes * pieces
+};
+
+enum CopyMode { kStore = 0, kLoad = 1, kPull = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared (this CTA), completion signalled on an mbarrier in bytes.  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // <= N groups still reading smem
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {  // <= N groups not yet complete (writes done)
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_na_v2(void* p, const uint2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                   : "memory");
+}
+__device__ __forceinline__ uint32_t ld_dsmem_u32(const void* local_smem_ptr, uint32_t rank) {
+  uint32_t remote, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+               : "=r"(remote)
+               : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// addressing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t paged_addr(const PagedSide& s, uint32_t plane, uint32_t slot) {
+  const uint32_t blk = slot / s.block_tokens;
+  const uint32_t off = slot - blk * s.block_tokens;
+  return __ldg(s.bases + plane) + static_cast<uint64_t>(blk) * s.block_stride +
+         static_cast<uint64_t>(off) * s.token_bytes;
+}
+__device__ __forceinline__ uint64_t chunk_addr(const ChunkSide& s, uint32_t plane, uint32_t tok) {
+  const uint32_t c = tok / s.chunk_tokens;
+  const uint32_t t = tok - c * s.chunk_tokens;
+  return __ldg(s.chunk_addrs + c) + static_cast<uint64_t>(plane) * s.slab_bytes +
+         static_cast<uint64_t>(t) * s.token_bytes;
+}
+
+struct Unit {
+  uint64_t src, dst;
+  uint32_t bytes;
+};
+
+template <int MODE>
+__device__ __forceinline__ Unit decode_unit(const CopyParams& p, uint32_t u) {
+  // plane fastest: consecutive units of one CTA stride across planes of the same run.
+  const uint32_t plane = u % p.n_planes;
+  const uint32_t t = u / p.n_planes;
+  const uint32_t piece = t % p.pieces;
+  const uint32_t r = t / p.pieces;
+  const Run run = p.runs[r];
+  const int32_t off = static_cast<int32_t>(piece * p.piece_tokens);
+  int32_t n = run.n - off;
+  n = n < 0 ? 0 : (n > static_cast<int32_t>(p.piece_tokens) ? static_cast<int32_t>(p.piece_tokens) : n);
+  Unit out;
+  out.bytes = static_cast<uint32_t>(n) * p.paged.token_bytes;
+  if (MODE == kStore) {
+    out.src = paged_addr(p.paged, plane, static_cast<uint32_t>(run.a + off));
+    out.dst = chunk_addr(p.chunk, plane, static_cast<uint32_t>(run.b + off));
+  } else if (MODE == kLoad) {
+    out.src = chunk_addr(p.chunk, plane, static_cast<uint32_t>(run.b + off));
+    out.dst = paged_addr(p.paged, plane, static_cast<uint32_t>(run.a + off));
+  } else {
+    out.src = paged_addr(p.peer, plane, static_cast<uint32_t>(run.a + off));
+    out.dst = paged_addr(p.paged, plane, static_cast<uint32_t>(run.b + off));
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RAW path, TMA-engine variant.  One warp per CTA, lane 0 does everything:
+//   iteration j:  (B) issue bulk load of unit j into stage j%S   (after the store that last used
+//                     that stage finished READING smem)
+//                 (A) wait for unit j-LAG's bytes, issue its bulk store, commit one group.
+// Loads in flight per CTA: LAG; stores in flight: S-LAG.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int S, int LAG>
+__global__ void __launch_bounds__(32) kv_bulk_copy_kernel(const CopyParams p, uint32_t stage_bytes) {
+  static_assert(LAG >= 1 && LAG < S, "need 1 <= LAG < S");
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);               // S mbarriers
+  uint64_t* dsts = reinterpret_cast<uint64_t*>(smem + 64);          // S pending dst addresses
+  uint32_t* lens = reinterpret_cast<uint32_t*>(smem + 64 + 8 * S);  // S pending lengths
+  uint8_t* stage0 = smem + 256;
+
+  if (threadIdx.x != 0) return;
+#pragma unroll
+  for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+  fence_mbar_init();
+
+  const uint32_t first = blockIdx.x;
+  const uint32_t step = gridDim.x;
+  const uint32_t n = first < p.total_units ? (p.total_units - first + step - 1) / step : 0;
+
+  for (uint32_t j = 0; j < n + LAG; ++j) {
+    if (j < n) {
+      const uint32_t s = j % S;
+      if (j >= S) bulk_wait_read<S - 1 - LAG>();  // store of unit j-S has drained its stage
+      const Unit u = decode_unit<MODE>(p, first + j * step);
+      dsts[s] = u.dst;
+      lens[s] = u.bytes;
+      if (u.bytes) bulk_g2s(stage0 + static_cast<size_t>(s) * stage_bytes,
+                            reinterpret_cast<const void*>(u.src), u.bytes, &full[s]);
+      mbar_arrive_expect_tx(&full[s], u.bytes);
+    }
+    if (j >= LAG) {
+      const uint32_t k = j - LAG;
+      const uint32_t s = k % S;
+      mbar_wait(&full[s], (k / S) & 1u);
+      const uint32_t bytes = lens[s];
+      if (bytes) bulk_s2g(reinterpret_cast<void*>(dsts[s]),
+                          stage0 + static_cast<size_t>(s) * stage_bytes, bytes);
+      bulk_commit();
+    }
+  }
+  bulk_wait_all<0>();  // every store has landed before the grid is considered complete
+}
+
+// ---------------------------------------------------------------------------------------------
+// RAW path, LSU variant: a CTA copies one unit at a time with 128-bit loads, 4 in flight/thread.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) kv_ldg_copy_kernel(const CopyParams p) {
+  for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x) {
+    const Unit u = decode_unit<MODE>(p, ui);
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(u.src);
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(u.dst);
+    const uint32_t nvec = u.bytes >> 4;
+    uint32_t i = threadIdx.x;
+    for (; i + 3 * 256 < nvec; i += 4 * 256) {
+      const uint4 a = ld_nc_v4(src + i), b = ld_nc_v4(src + i + 256);
+      const uint4 c = ld_nc_v4(src + i + 512), d = ld_nc_v4(src + i + 768);
+      st_na_v4(dst + i, a);
+      st_na_v4(dst + i + 256, b);
+      st_na_v4(dst + i + 512, c);
+      st_na_v4(dst + i + 768, d);
+    }
+    for (; i < nvec; i += 256) st_na_v4(dst + i, ld_nc_v4(src + i));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP8 store.  grid = (kCluster * n_slabs), cluster (kCluster,1,1); slab = (chunk c, plane).
+// CTA `rank` owns tokens [rank*W, rank*W+W) of the chunk, W = C / kCluster.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCluster = 8;
+constexpr int kFp8Threads = 256;
+constexpr int kMaxHeads = 64;
+
+struct Fp8StoreParams {
+  PagedSide paged;
+  const Run* runs;                // sorted by b
+  const uint32_t* chunk_run_off;  // [n_chunks+1] run range of each chunk
+  const uint64_t* chunk_addrs;    // [n_chunks] destination of each chunk
+  uint32_t n_chunks, n_planes;
+  uint32_t chunk_tokens;          // C
+  uint32_t n_tokens;              // op length
+  uint32_t n_heads, head_bytes;   // H, D*2
+  uint64_t slab_q_bytes;          // C * H * D   (e4m3 bytes per slab)
+  uint64_t scales_off;            // byte offset of the (planes, H) fp32 scales inside a chunk
+};
+
+__device__ __forceinline__ uint32_t absmax_u16x2(uint32_t acc, uint32_t w) {
+  return __vmaxu2(acc, w & 0x7fff7fffu);
+}
+
+// e4m3 of 8 bf16 scaled by inv (fp32 multiply, RN, satfinite) -> 8 bytes.
+__device__ __forceinline__ uint2 quant8(const uint4& v, float inv) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float a0 = __uint_as_float(w[2 * i] << 16) * inv;
+    const float a1 = __uint_as_float(w[2 * i] & 0xffff0000u) * inv;
+    const float b0 = __uint_as_float(w[2 * i + 1] << 16) * inv;
+    const float b1 = __uint_as_float(w[2 * i + 1] & 0xffff0000u) * inv;
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a0, a1), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(b0, b1), __NV_SATFINITE, __NV_E4M3);
+    o[i] = lo | (hi << 16);
+  }
+  return make_uint2(o[0], o[1]);
+}
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
+    kv_fp8_store_kernel(const Fp8StoreParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_absmax[kMaxHeads];  // bf16 |x| bits (integer order == magnitude order)
+  __shared__ float s_inv[kMaxHeads];
+
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t slab = blockIdx.x / kCluster;
+  const uint32_t c = slab / p.n_planes;
+  const uint32_t plane = slab - c * p.n_planes;
+  const uint32_t W = p.chunk_tokens / kCluster;
+  const uint32_t tb = p.paged.token_bytes;
+  const uint32_t win_lo = c * p.chunk_tokens + rank * W;  // op-relative token index
+  uint32_t n_valid = 0;
+  if (win_lo < p.n_tokens) n_valid = min(W, p.n_tokens - win_lo);
+  const uint32_t chunk_hi = min((c + 1) * p.chunk_tokens, p.n_tokens);
+  if (win_lo + n_valid > chunk_hi) n_valid = chunk_hi > win_lo ? chunk_hi - win_lo : 0;
+
+  if (threadIdx.x < kMaxHeads) s_absmax[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    uint32_t total = 0;
+    const uint32_t r0 = p.chunk_run_off[c], r1 = p.chunk_run_off[c + 1];
+    for (uint32_t r = r0; r < r1; ++r) {
+      const Run run = p.runs[r];
+      const int32_t lo = max(run.b, static_cast<int32_t>(win_lo));
+      const int32_t hi = min(run.b + run.n, static_cast<int32_t>(win_lo + n_valid));
+      if (hi <= lo) continue;
+      const uint32_t bytes = static_cast<uint32_t>(hi - lo) * tb;
+      bulk_g2s(smem + static_cast<size_t>(lo - static_cast<int32_t>(win_lo)) * tb,
+               reinterpret_cast<const void*>(
+                   paged_addr(p.paged, plane, static_cast<uint32_t>(run.a + (lo - run.b)))),
+               bytes, &bar);
+      total += bytes;
+    }
+    mbar_arrive_expect_tx(&bar, total);
+  }
+  __syncthreads();  // barrier init + s_absmax zero visible
+  mbar_wait(&bar, 0);
+
+  // ---- per-head absmax over this CTA's tokens: a thread's 16-byte column has a fixed head ----
+  // When a token has fewer than 256 vectors the spare threads split the tokens between them.
+  const uint32_t vpt = tb >> 4;  // 16-byte vectors per token
+  const uint32_t groups = vpt < kFp8Threads ? kFp8Threads / vpt : 1;
+  const uint32_t grp = threadIdx.x / vpt;
+  if (grp < groups) {
+    const uint32_t col_step = groups == 1 ? kFp8Threads : vpt;
+    for (uint32_t col = threadIdx.x - grp * vpt; col < vpt; col += col_step) {
+      uint32_t acc = 0;
+      const uint8_t* q = smem + static_cast<size_t>(col) * 16;
+      for (uint32_t t = grp; t < n_valid; t += groups) {
+        const uint4 v = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(t) * tb);
+        acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(acc, v.x), v.y), v.z), v.w);
+      }
+      const uint32_t m = max(acc & 0xffffu, acc >> 16);
+      atomicMax(&s_absmax[(col * 16) / p.head_bytes], m);
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();  // every CTA's s_absmax is final and visible cluster-wide
+
+  if (threadIdx.x < p.n_heads) {
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < kCluster; ++r) m = max(m, ld_dsmem_u32(&s_absmax[threadIdx.x], r));
+    const float amax = __uint_as_float(m << 16);
+    const float inv = (m == 0) ? 1.0f : __fdiv_rn(448.0f, amax);
+    s_inv[threadIdx.x] = inv;
+    if (rank == 0) {
+      float* scales = reinterpret_cast<float*>(p.chunk_addrs[c] + p.scales_off);
+      scales[plane * p.n_heads + threadIdx.x] = (m == 0) ? 1.0f : __fdiv_rn(amax, 448.0f);
+    }
+  }
+  __syncthreads();
+
+  // ---- quantise from smem, 8-byte coalesced stores ----
+  uint8_t* out = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
+                                            static_cast<uint64_t>(rank * W) * (tb >> 1));
+  const uint32_t nvec = n_valid * vpt;
+  for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+    const uint32_t col = i % vpt;
+    const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(i) * 16);
+    st_na_v2(out + static_cast<size_t>(i) * 8, quant8(v, s_inv[(col * 16) / p.head_bytes]));
+  }
+  cluster_sync_all();  // keep smem alive until every peer CTA has read our s_absmax
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP8 load: one CTA per (run, plane) unit; e4m3 * scale -> bf16 (RN) into the pages.
+// ---------------------------------------------------------------------------------------------
+struct Fp8LoadParams {
+  PagedSide paged;
+  const Run* runs;
+  const uint64_t* chunk_addrs;
+  uint32_t n_runs, n_planes;
+  uint32_t chunk_tokens;
+  uint32_t n_heads, head_bytes;  // head_bytes = D*2 (bf16 side)
+  uint64_t slab_q_bytes;
+  uint64_t scales_off;
+  uint32_t total_units;
+};
+
+__device__ __forceinline__ uint4 dequant8(const uint2& q, float scale) {
+  const uint32_t w[2] = {q.x, q.y};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const __half2_raw h0 = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w[i] & 0xffffu), __NV_E4M3);
+    const __half2_raw h1 = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w[i] >> 16), __NV_E4M3);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+    const __nv_bfloat162 b0 = __floats2bfloat162_rn(f0.x * scale, f0.y * scale);
+    const __nv_bfloat162 b1 = __floats2bfloat162_rn(f1.x * scale, f1.y * scale);
+    o[2 * i] = *reinterpret_cast<const uint32_t*>(&b0);
+    o[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&b1);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(kFp8Threads) kv_fp8_load_kernel(const Fp8LoadParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float s_scale[kMaxHeads];
+  const uint32_t tb = p.paged.token_bytes;  // bf16 bytes per token
+  const uint32_t qtb = tb >> 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  uint32_t phase = 0;
+  for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x, phase ^= 1u) {
+    const uint32_t plane = ui % p.n_planes;
+    const Run run = p.runs[ui / p.n_planes];
+    const uint32_t c = static_cast<uint32_t>(run.b) / p.chunk_tokens;
+    const uint32_t t = static_cast<uint32_t>(run.b) - c * p.chunk_tokens;
+    const uint64_t cbase = __ldg(p.chunk_addrs + c);
+    const uint32_t qbytes = static_cast<uint32_t>(run.n) * qtb;
+    if (threadIdx.x == 0) {
+      bulk_g2s(smem, reinterpret_cast<const void*>(cbase + static_cast<uint64_t>(plane) * p.slab_q_bytes +
+                                                   static_cast<uint64_t>(t) * qtb),
+               qbytes, &bar);
+      mbar_arrive_expect_tx(&bar, qbytes);
+    }
+    if (threadIdx.x < p.n_heads)
+      s_scale[threadIdx.x] =
+          reinterpret_cast<const float*>(cbase + p.scales_off)[plane * p.n_heads + threadIdx.x];
+    __syncthreads();
+    mbar_wait(&bar, phase);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(paged_addr(p.paged, plane, static_cast<uint32_t>(run.a)));
+    const uint32_t vpt = tb >> 4;
+    const uint32_t nvec = static_cast<uint32_t>(run.n) * vpt;
+    for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+      const uint32_t col = i % vpt;
+      const uint2 q = *reinterpret_cast<const uint2*>(smem + static_cast<size_t>(i) * 8);
+      st_na_v4(dst + static_cast<size_t>(i) * 16, dequant8(q, s_scale[(col * 16) / p.head_bytes]));
+    }
+    __syncthreads();  // smem + s_scale reusable
+  }
+}
+
+}  // namespace b200kv

@@ -1,0 +1,166 @@
+"""Host pool + index (CPU): writer/reader protocol, LRU, leases, pins, cross-process sharing."""
+import multiprocessing as mp
+import time
+
+import numpy as np
+import pytest
+
+from b200kv import B200KVError, KVPool, _lib
+
+SLOT = 4096
+
+
+def mk(n_slots=4, name=None):
+    return KVPool(name, n_slots * SLOT, SLOT, _lib.POOL_CREATE)
+
+
+def put(pool, key, n_tok=256, fill=None, owner=0):
+    slot = pool.reserve(key, n_tok, 0, owner)
+    if fill is not None:
+        pool.slot_view(slot)[:] = fill
+    pool.commit(key)
+    return slot
+
+
+def test_reserve_commit_lookup_prefix_semantics():
+    p = mk()
+    keys = np.array([11, 22, 33], dtype=np.uint64)
+    ct = np.array([256, 256, 100], dtype=np.int32)
+    assert p.lookup(keys, ct) == (0, 0)
+    put(p, 11)
+    put(p, 33, 100)
+    assert p.lookup(keys, ct) == (1, 256)          # stops at the first miss (22)
+    s = p.reserve(22, 256)
+    assert p.lookup(keys, ct) == (1, 256)          # WRITING chunks are invisible
+    p.commit(22)
+    assert p.lookup(keys, ct) == (3, 612)
+    ct_bad = np.array([256, 256, 101], dtype=np.int32)
+    assert p.lookup(keys, ct_bad) == (2, 512)      # partial chunk must match its token count
+    st = p.stats()
+    assert st["n_used"] == 3 and st["n_stored_chunks"] == 3 and st["n_slots"] == 4
+    assert s < 4
+    p.close()
+
+
+def test_duplicate_reserve_and_abort():
+    p = mk()
+    p.reserve(5, 256)
+    with pytest.raises(B200KVError) as ei:
+        p.reserve(5, 256)
+    assert ei.value.code == _lib.EEXIST
+    p.abort(5)
+    assert p.stats()["n_used"] == 0
+    put(p, 5)
+    with pytest.raises(B200KVError):
+        p.commit(5)                                # already READY
+    p.close()
+
+
+def test_lru_eviction_order_and_touch():
+    p = mk(3)
+    for k in (1, 2, 3):
+        put(p, k)
+    p.lookup(np.array([1], np.uint64), np.array([256], np.int32))   # touch 1 -> LRU order 2,3,1
+    put(p, 4)                                                        # evicts 2
+    one = lambda k: p.lookup(np.array([k], np.uint64), np.array([256], np.int32))[0]
+    assert one(2) == 0 and one(3) == 1 and one(1) == 1 and one(4) == 1
+    assert p.stats()["n_evicted_chunks"] == 1
+    p.close()
+
+
+def test_pins_and_leases_block_eviction():
+    p = mk(2)
+    put(p, 1)
+    put(p, 2)
+    slot, n, fmt = p.acquire(1)
+    assert n == 256 and fmt == 0
+    p.lookup(np.array([2], np.uint64), np.array([256], np.int32), lease_ms=60000)
+    with pytest.raises(B200KVError) as ei:
+        p.reserve(3, 256)                          # 1 pinned, 2 leased -> nothing evictable
+    assert ei.value.code == _lib.ENOSPC and p.stats()["n_dropped_chunks"] == 1
+    p.release(1)
+    put(p, 3)                                      # evicts 1 (unpinned), not the leased 2
+    assert p.lookup(np.array([2], np.uint64), np.array([256], np.int32))[0] == 1
+    assert p.lookup(np.array([1], np.uint64), np.array([256], np.int32))[0] == 0
+    p.close()
+
+
+def test_lease_expires():
+    p = mk(1)
+    put(p, 1)
+    p.lookup(np.array([1], np.uint64), np.array([256], np.int32), lease_ms=30)
+    with pytest.raises(B200KVError):
+        p.reserve(2, 256)
+    time.sleep(0.06)
+    put(p, 2)
+    p.close()
+
+
+def test_many_keys_tombstone_rebuild():
+    p = mk(8)
+    rng = np.random.default_rng(0)
+    live = []
+    for i in range(2000):
+        k = int(rng.integers(1, 2 ** 63))
+        put(p, k)
+        live.append(k)
+        live = live[-8:]
+    for k in live:
+        assert p.lookup(np.array([k], np.uint64), np.array([256], np.int32))[0] == 1
+    assert p.stats()["n_used"] == 8
+    assert p.clear() and p.stats()["n_used"] == 0
+    p.close()
+
+
+def test_owner_lookup():
+    p = mk()
+    put(p, 7, owner=3)
+    put(p, 8, owner=5)
+    hits, owners = p.lookup_owner(np.array([7, 8, 9], np.uint64))
+    assert hits == 2 and list(owners) == [3, 5]
+    p.close()
+
+
+def _child(name, q):
+    try:
+        c = KVPool(name, 0, SLOT, _lib.POOL_ATTACH)
+        hit = c.lookup(np.array([42, 43], np.uint64), np.array([256, 7], np.int32))
+        slot, n, _ = c.acquire(43)
+        data = bytes(c.slot_view(slot)[:8])
+        c.release(43)
+        put(c, 44, 256, fill=9)
+        c.close()
+        q.put((hit, n, data))
+    except Exception as e:  # pragma: no cover
+        q.put(repr(e))
+
+
+def test_shared_segment_across_processes(shm_name):
+    """Scheduler-role and worker-role connectors (and other replicas) share one index."""
+    p = KVPool(shm_name, 4 * SLOT, SLOT, _lib.POOL_CREATE)
+    put(p, 42, 256, fill=1)
+    put(p, 43, 7, fill=5)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    proc = ctx.Process(target=_child, args=(shm_name, q))
+    proc.start()
+    res = q.get(timeout=60)
+    proc.join(60)
+    assert res == ((2, 263), 7, b"\x05" * 8), res
+    slot, n, _ = p.acquire(44)                     # written by the other process
+    assert n == 256 and int(p.slot_view(slot)[0]) == 9
+    p.release(44)
+    with pytest.raises(B200KVError):
+        KVPool(shm_name, 4 * SLOT, SLOT, _lib.POOL_CREATE)      # exclusive create
+    with pytest.raises(B200KVError):
+        KVPool(shm_name, 0, SLOT * 2, _lib.POOL_ATTACH)          # geometry mismatch
+    p.close()
+
+
+def test_bad_arguments():
+    with pytest.raises(B200KVError):
+        KVPool(None, 10, 4096, _lib.POOL_CREATE)                 # pool smaller than a slot
+    with pytest.raises(B200KVError):
+        KVPool("no-leading-slash", 8192, 4096, _lib.POOL_CREATE)
+    with pytest.raises(B200KVError):
+        KVPool("/b200kv-does-not-exist", 0, 0, _lib.POOL_ATTACH)
