@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — KV offload hot path on B200 (driver contract: one JSON line on rank 0).
+
+Workload (BASELINE.json configs[1], "Llama-3-8B, 1 replica on 1xB200, CPU-RAM offload,
+multi-round-qa 4-turn 2K-ctx"): one step = the KV traffic of one scheduling wave of the
+multi-round-QA harness — 16 user sessions x 2048-token context, Llama-3-8B KV geometry
+(L=32, H_kv=8, D=128, bf16, block 16, chunk 256 => 128 KiB/token, 4 GiB per direction per step):
+
+  e2e    (headline): every session is stored  (paged HBM -> fused gather -> pinned host pool) and
+         then retrieved (pinned host pool -> staging -> scatter into *other* pages) through the
+         reference-facing engine calls (KVEngine.store / .retrieve == lmcache_engine.store /
+         .retrieve); D2H and H2D are inside the timed region; fresh token ids every step so every
+         chunk is really written (LRU eviction included).
+  value  : the same 32768 tokens gathered into / scattered from a DEVICE buffer (HBM only).
+  roofline: dominant kernel = RAW gather (kv_bulk_copy_kernel<store>); algorithmic bytes =
+         262144 B/token x tokens per launch / CUDA-event duration of that launch.
+
+metric = KV payload GB/s (store+retrieve payload bytes / time).  `--impl reference` times the CPU
+oracle port (oracle/liboracle.so; the lmcache wheel is absent from this image) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "production-stack_b200"))
+
+L, H, D, BS, C = 32, 8, 128, 16, 256
+NB = 8192                     # 16 GiB paged cache
+SESSIONS, CTX = 16, 2048      # one wave of the 2K-ctx multi-round-QA config
+TOKEN_BYTES_ALL = 2 * L * H * D * 2   # 131072 B payload per token (bf16)
+ALGO_BYTES_PER_TOKEN = 2 * TOKEN_BYTES_ALL  # HBM read + HBM write of the gather kernel
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def session_tokens(rank: int, step: int, s: int) -> np.ndarray:
+    """Deterministic synthetic token ids, unique per (rank, step, session) so keys are fresh."""
+    base = np.arange(CTX, dtype=np.int64)
+    return ((base * 2654435761 + (rank * 1000003 + step * 10007 + s) * 97) % 128256).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024):
+    """store+retrieve of `sessions` x 2K-ctx requests per step with oracle/liboracle.so (gather
+    into a host chunk buffer = the CPU pool, scatter back into other pages).  Returns
+    (GB/s payload, ms/step, threads, sample description)."""
+    from oracle import kv_oracle as ko
+    from tests import oracle_c
+    rng = np.random.default_rng(0)
+    layers = [rng.integers(0, 2 ** 16, (2, nb, BS, H, D), dtype=np.uint16) for _ in range(L)]
+    perm = np.random.default_rng(1234).permutation(nb)
+    dperm = np.random.default_rng(4321).permutation(nb)
+    nblk = CTX // BS
+    maps = [(ko.slot_mapping_from_blocks(perm[s * nblk:(s + 1) * nblk], BS, CTX),
+             ko.slot_mapping_from_blocks(dperm[s * nblk:(s + 1) * nblk], BS, CTX)) for s in range(sessions)]
+    threads = oracle_c.lib().oracle_num_threads()
+    keys_out = np.zeros(CTX // C, dtype=np.uint64)
+
+    def one_step(step):
+        for s, (sm, dm) in enumerate(maps):
+            toks = session_tokens(0, step, s)
+            oracle_c.lib().oracle_chunk_keys(toks.ctypes.data, CTX, C, 0, 1, keys_out.ctypes.data)
+            chunks, cb, so = oracle_c.gather(layers, sm, C, "raw")
+            oracle_c.scatter(layers, dm, C, chunks, cb, so, "raw")
+
+    for w in range(warmup):
+        one_step(w)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one_step(warmup + k)
+    dt = time.perf_counter() - t0
+    payload = 2 * sessions * CTX * TOKEN_BYTES_ALL * steps
+    sample = f"{sessions} sessions x {CTX} tokens per step (of {SESSIONS}), paged cache {nb} blocks in host RAM, RAW bf16"
+    return payload / dt / 1e9, dt / steps * 1e3, threads, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    gbps, ms, threads, sample = cpu_oracle_run(args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "kv_offload_GBps", "value": gbps, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference path = third-party lmcache wheel, absent from this image; this is the oracle port "
+                "(oracle/kv_oracle.c) of its store/retrieve on host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "multi-round-qa 2K-ctx wave: 16 sessions x 2048 tokens, Llama-3-8B KV "
+                        "(L32 H8 D128 bf16, block 16, chunk 256), store+retrieve per step",
+            "tokens_per_step_per_gpu": SESSIONS * CTX, "paged_blocks": NB,
+            "l2_policy": "inputs (4 GiB/direction/step) larger than L2; no explicit flush",
+            "parallelism": f"{n_gpus} independent replicas, one per GPU, no collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    ge.build(quiet=True)
+    from b200kv import FMT_FP8, FMT_RAW, KVEngine, KVGeometry, KVPool
+    from oracle import kv_oracle as ko  # slot-mapping helper + cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the b200kv engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    geom = KVGeometry(L, H, D, NB, BS, C, 2, 0, FMT_RAW)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    caches = [torch.randn((2, NB, BS, H, D), generator=g, device=dev, dtype=torch.float32).bfloat16()
+              for _ in range(L)]
+    n_chunks_step = SESSIONS * CTX // C
+    pool = KVPool(None, (n_chunks_step + n_chunks_step // 2) * geom.chunk_bytes, geom.chunk_bytes, 1)
+    eng = KVEngine(geom, pool, local, staging_bytes=32 * geom.chunk_bytes, owner=rank)
+    eng.register_kv_caches(caches)
+
+    perm = torch.randperm(NB, generator=torch.Generator().manual_seed(1234)).numpy()
+    dperm = torch.randperm(NB, generator=torch.Generator().manual_seed(4321)).numpy()
+    nblk = CTX // BS
+    src_maps = [ko.slot_mapping_from_blocks(perm[s * nblk:(s + 1) * nblk], BS, CTX) for s in range(SESSIONS)]
+    dst_maps = [ko.slot_mapping_from_blocks(dperm[s * nblk:(s + 1) * nblk], BS, CTX) for s in range(SESSIONS)]
+    all_src = np.concatenate(src_maps)
+    all_dst = np.concatenate(dst_maps)
+    stream = torch.cuda.current_stream()
+
+    # ---- e2e leg: store + retrieve through the engine, host pool in the loop ------------------
+    def e2e_step(step):
+        toks = [session_tokens(rank, step, s) for s in range(SESSIONS)]
+        for s in range(SESSIONS):
+            eng.store(toks[s], None, src_maps[s], stream=stream)
+        eng.wait_all()                      # every chunk committed to the host index
+        n = 0
+        for s in range(SESSIONS):
+            n += int(eng.retrieve(toks[s], None, dst_maps[s], stream=stream).sum())
+        return n
+
+    for w in range(args.warmup):
+        assert e2e_step(w) == SESSIONS * CTX
+    torch.cuda.synchronize()
+    st0 = eng.stats()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for k in range(args.steps):
+        got = e2e_step(args.warmup + k)
+        assert got == SESSIONS * CTX, got
+    eng.wait_all()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    st1 = eng.stats()
+    e2e_payload = 2 * SESSIONS * CTX * TOKEN_BYTES_ALL
+    e2e_gbps = world * e2e_payload / (e2e_ms * 1e-3) / 1e9
+
+    # ---- value leg: the same tokens, device-resident (HBM only) ---------------------------------
+    dbuf = torch.empty(n_chunks_step * geom.chunk_bytes, dtype=torch.uint8, device=dev)
+
+    def dev_step():
+        eng.gather(all_src, dbuf.data_ptr(), stream)
+        eng.scatter(all_dst, dbuf.data_ptr(), stream)
+
+    for w in range(args.warmup):
+        dev_step()
+    torch.cuda.synchronize()
+    st2 = eng.stats()
+    gather_ms = []
+    barrier()
+    ev0.record(stream)
+    for k in range(args.steps):
+        dev_step()
+        # kernel-only durations of this step's launches (CUDA events recorded by the library on
+        # the launching stream); reading them synchronises the stream, which the next launch
+        # would do anyway through the stream order.
+        gather_ms.append((eng.last_kernel_ms(0), eng.last_kernel_ms(1)))
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    st3 = eng.stats()
+    clocks = sampler.stop() if sampler else None
+    value_gbps = world * e2e_payload / (dev_ms * 1e-3) / 1e9
+    g_ms = float(np.mean([a for a, _ in gather_ms]))
+    s_ms = float(np.mean([b for _, b in gather_ms]))
+
+    # ---- fp8 leg (extra, not the headline): same wave in FMT_FP8, device-resident + e2e --------
+    fp8 = None
+    if not args.no_fp8:
+        eng.close()
+        pool.close()
+        g8 = KVGeometry(L, H, D, NB, BS, C, 2, 0, FMT_FP8)
+        pool8 = KVPool(None, (n_chunks_step + n_chunks_step // 2) * g8.chunk_bytes, g8.chunk_bytes, 1)
+        e8 = KVEngine(g8, pool8, local, staging_bytes=32 * g8.chunk_bytes, owner=rank)
+        e8.register_kv_caches(caches)
+        b8 = torch.empty(n_chunks_step * g8.chunk_bytes, dtype=torch.uint8, device=dev)
+
+        def fp8_e2e(step):
+            toks = [session_tokens(rank, 1000 + step, s) for s in range(SESSIONS)]
+            for s in range(SESSIONS):
+                e8.store(toks[s], None, src_maps[s], stream=stream)
+            e8.wait_all()
+            for s in range(SESSIONS):
+                e8.retrieve(toks[s], None, dst_maps[s], stream=stream)
+
+        for w in range(max(args.warmup, 1)):
+            fp8_e2e(w)
+            e8.gather(all_src, b8.data_ptr(), stream)
+            e8.scatter(all_dst, b8.data_ptr(), stream)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for k in range(args.steps):
+            fp8_e2e(args.warmup + k)
+        e8.wait_all()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        f_e2e_ms = ev0.elapsed_time(ev1) / args.steps
+        km = []
+        for k in range(args.steps):
+            e8.gather(all_src, b8.data_ptr(), stream)
+            e8.scatter(all_dst, b8.data_ptr(), stream)
+            km.append((e8.last_kernel_ms(0), e8.last_kernel_ms(1)))
+        torch.cuda.synchronize()
+        fp8 = {"e2e_tokens_per_s": SESSIONS * CTX * 2 / (f_e2e_ms * 1e-3),
+               "e2e_equiv_bf16_GBps": e2e_payload / (f_e2e_ms * 1e-3) / 1e9,
+               "pack_kernel_ms": float(np.mean([a for a, _ in km])),
+               "unpack_kernel_ms": float(np.mean([b for _, b in km])),
+               "pack_kernel_algo_GBps": SESSIONS * CTX * (TOKEN_BYTES_ALL * 3 // 2 + 8) / (np.mean([a for a, _ in km]) * 1e-3) / 1e9}
+        e8.close()
+        pool8.close()
+    else:
+        eng.close()
+        pool.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    launch_tokens = SESSIONS * CTX
+    achieved = launch_tokens * ALGO_BYTES_PER_TOKEN / (g_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_gather.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu_gbps, cpu_ms, cpu_threads, cpu_sample = cpu_oracle_run(3, 1)
+    line = {
+        "metric": "kv_offload_GBps", "value": value_gbps, "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e_gbps, "unit": "GB/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,
+                "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps,
+                "kv_ttft_ms_per_2k_ctx_request": e2e_ms / (2 * SESSIONS)},
+        "gpu_launches": (st1["n_kernel_launches"] - st0["n_kernel_launches"]) + (st3["n_kernel_launches"] - st2["n_kernel_launches"]),
+        "roofline": {"bound": "hbm", "kernel": "kv_bulk_copy_kernel<store> (RAW gather, device-resident leg)",
+                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                     "peak_kind": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
+                     "launch_ms": g_ms, "scatter_launch_ms": s_ms,
+                     "scatter_achieved": launch_tokens * ALGO_BYTES_PER_TOKEN / (s_ms * 1e-3) / 1e9,
+                     "algo_bytes_per_launch": launch_tokens * ALGO_BYTES_PER_TOKEN, "traffic": traffic},
+        "cpu_baseline": {"value": cpu_gbps, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
+                         "sample": cpu_sample, "ms_per_step": cpu_ms},
+        "clocks": clocks,
+        "fp8": fp8,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-fp8", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -586,9 +586,16 @@ extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool
     if (ps.slot_bytes < g.chunk_bytes) return B200KV_EINVAL;
     // Pin the (possibly shared) pool for this process so D2H/H2D run at full PCIe speed and
     // asynchronously.  Portable: every replica on the box registers the same segment.
-    CU_TRY(cudaHostRegister(base, bytes, cudaHostRegisterPortable));
-    ctx->pool_registered = true;
-    ctx->pool_base = base;
+    const cudaError_t re = cudaHostRegister(base, bytes, cudaHostRegisterPortable);
+    if (re == cudaSuccess) {
+      ctx->pool_registered = true;
+      ctx->pool_base = base;
+    } else if (re == cudaErrorHostMemoryAlreadyRegistered) {
+      cudaGetLastError();  // another engine of this process (e.g. a second GPU) pinned it already
+    } else {
+      set_err("cudaHostRegister(pool)", re, __LINE__);
+      return B200KV_ENODEV;
+    }
   }
   *out = ctx.release();
   return B200KV_OK;
