@@ -204,7 +204,10 @@ def run_ours(args):
               for _ in range(L)]
     n_chunks_step = SESSIONS * CTX // C
     pool = KVPool(None, (n_chunks_step + n_chunks_step // 2) * geom.chunk_bytes, geom.chunk_bytes, 1)
-    eng = KVEngine(geom, pool, local, staging_bytes=32 * geom.chunk_bytes, owner=rank)
+    # staging ring sized to absorb one whole wave per direction (store half + load half): a gather
+    # never has to wait for the PCIe drain of an earlier session, so the compute stream is never
+    # held back by store traffic (production default is 1 GiB, B200KV_STAGING_MB)
+    eng = KVEngine(geom, pool, local, staging_bytes=2 * n_chunks_step * geom.chunk_bytes, owner=rank)
     eng.register_kv_caches(caches)
 
     perm = torch.randperm(NB, generator=torch.Generator().manual_seed(1234)).numpy()
@@ -218,12 +221,13 @@ def run_ours(args):
 
     # ---- e2e leg: store + retrieve through the engine, host pool in the loop ------------------
     def e2e_step(step):
+        # every session is stored, and retrieved as soon as ITS store has been committed to the
+        # host index; retrieves of early sessions overlap the D2H of later ones (PCIe is full duplex)
         toks = [session_tokens(rank, step, s) for s in range(SESSIONS)]
-        for s in range(SESSIONS):
-            eng.store(toks[s], None, src_maps[s], stream=stream)
-        eng.wait_all()                      # every chunk committed to the host index
+        tickets = [eng.store(toks[s], None, src_maps[s], stream=stream) for s in range(SESSIONS)]
         n = 0
         for s in range(SESSIONS):
+            eng.wait(tickets[s])
             n += int(eng.retrieve(toks[s], None, dst_maps[s], stream=stream).sum())
         return n
 
@@ -284,16 +288,15 @@ def run_ours(args):
         pool.close()
         g8 = KVGeometry(L, H, D, NB, BS, C, 2, 0, FMT_FP8)
         pool8 = KVPool(None, (n_chunks_step + n_chunks_step // 2) * g8.chunk_bytes, g8.chunk_bytes, 1)
-        e8 = KVEngine(g8, pool8, local, staging_bytes=32 * g8.chunk_bytes, owner=rank)
+        e8 = KVEngine(g8, pool8, local, staging_bytes=2 * n_chunks_step * g8.chunk_bytes, owner=rank)
         e8.register_kv_caches(caches)
         b8 = torch.empty(n_chunks_step * g8.chunk_bytes, dtype=torch.uint8, device=dev)
 
         def fp8_e2e(step):
             toks = [session_tokens(rank, 1000 + step, s) for s in range(SESSIONS)]
+            tickets = [e8.store(toks[s], None, src_maps[s], stream=stream) for s in range(SESSIONS)]
             for s in range(SESSIONS):
-                e8.store(toks[s], None, src_maps[s], stream=stream)
-            e8.wait_all()
-            for s in range(SESSIONS):
+                e8.wait(tickets[s])
                 e8.retrieve(toks[s], None, dst_maps[s], stream=stream)
 
         for w in range(max(args.warmup, 1)):

@@ -1,0 +1,282 @@
+"""Scheduler-side and worker-side state machines of the connector, free of vLLM imports so they
+can be unit-tested against fake ``SchedulerOutput``s on CPU.
+
+Behavioural spec: vLLM's vendored LMCache adapter
+(vllm/distributed/kv_transfer/kv_connector/v1/lmcache_integration/vllm_v1_adapter.py):
+
+* which tokens a step saves                         — ReqMeta.from_request_tracker  :270-399
+* lookup + "recompute the last token" rule          — get_num_new_matched_tokens    :1141-1228
+* update_state_after_alloc / can_load               — :1231-1293
+* build_connector_meta (new, cached, finished reqs) — :1296-1407
+* start_load_kv masks / retrieve call               — :798-905
+* wait_for_save masks / store call                  — :1033-1128
+
+Restated, not copied: metadata carries block ids (16x smaller than a slot mapping to pickle
+across the scheduler->worker boundary); the slot mapping slot[i] = block[i//bs]*bs + i%bs
+(:368-375) is expanded on the worker.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class LoadSpec:
+    vllm_cached_tokens: int      # tokens vLLM's own prefix cache already holds
+    external_cached_tokens: int  # tokens the pool holds (whole chunks, maybe a partial tail)
+    can_load: bool = False       # set once the scheduler allocated blocks for them
+
+
+@dataclass
+class SaveSpec:
+    skip_leading_tokens: int     # already saved (chunk aligned by the worker)
+    can_save: bool
+
+
+@dataclass
+class ReqMeta:
+    req_id: str
+    token_ids: np.ndarray        # int32, the tokens this step may save / load
+    block_ids: list[int]
+    is_last_prefill: bool = False
+    save_spec: SaveSpec | None = None
+    load_spec: LoadSpec | None = None
+
+    def slot_mapping(self, block_size: int) -> np.ndarray:
+        b = np.asarray(self.block_ids, dtype=np.int64)
+        sm = (b[:, None] * block_size + np.arange(block_size, dtype=np.int64)[None, :]).reshape(-1)
+        return sm[: len(self.token_ids)]
+
+
+@dataclass
+class RequestTracker:
+    req_id: str
+    prompt_len: int
+    token_ids: list[int]
+    allocated_block_ids: list[int]
+    num_saved_tokens: int = 0
+    is_decode_phase: bool = False
+    skip_save: bool = False
+
+    def update(self, new_token_ids, new_block_ids, resumed: bool = False):
+        """A running request was scheduled again (adapter :214-245)."""
+        self.token_ids.extend(new_token_ids)
+        if new_block_ids is None:
+            new_block_ids = []
+        elif isinstance(new_block_ids, tuple):
+            new_block_ids = new_block_ids[0] if len(new_block_ids) else []
+        if resumed:
+            self.allocated_block_ids = list(new_block_ids)
+        else:
+            self.allocated_block_ids.extend(new_block_ids)
+        if len(new_token_ids) == 1:
+            self.is_decode_phase = True
+
+
+def first_group(block_ids):
+    """vLLM >= 0.9 hands block ids as one list per KV-cache group; single-group models only."""
+    if block_ids is None:
+        return []
+    if isinstance(block_ids, tuple) or (len(block_ids) and isinstance(block_ids[0], (list, tuple))):
+        return list(block_ids[0]) if len(block_ids) else []
+    return list(block_ids)
+
+
+def make_req_meta(tracker: RequestTracker, block_size: int, chunk: int, load_spec: LoadSpec | None,
+                  discard_partial_chunks: bool, save_decode_cache: bool = False) -> ReqMeta | None:
+    """What this step may save / load for one request (adapter :270-399)."""
+    n_in = len(tracker.token_ids)
+    is_last_prefill = n_in == tracker.prompt_len
+    skip_leading = tracker.num_saved_tokens
+    next_boundary = -(-(tracker.num_saved_tokens + 1) // chunk) * chunk
+    skip_save = (tracker.skip_save
+                 or (tracker.num_saved_tokens > 0 and n_in < next_boundary)
+                 or (tracker.is_decode_phase and not save_decode_cache))
+    if skip_save and load_spec is None:
+        return None
+    n_save = (n_in // chunk * chunk) if (not is_last_prefill or discard_partial_chunks) else n_in
+    if not skip_save:
+        tracker.num_saved_tokens = n_save
+    if load_spec is not None and not load_spec.can_load:
+        load_spec = None
+    n_tok = n_save
+    if load_spec is not None:
+        n_tok = max(n_tok, min(load_spec.external_cached_tokens, n_in))
+    capacity = len(tracker.allocated_block_ids) * block_size
+    n_tok = min(n_tok, capacity)
+    return ReqMeta(req_id=tracker.req_id,
+                   token_ids=np.asarray(tracker.token_ids[:n_tok], dtype=np.int32),
+                   block_ids=list(tracker.allocated_block_ids),
+                   is_last_prefill=is_last_prefill,
+                   save_spec=SaveSpec(skip_leading, (not skip_save) and n_save > 0),
+                   load_spec=load_spec)
+
+
+class SchedulerState:
+    """Scheduler-role half.  `lookup(token_ids) -> hit tokens` is injected (pool index)."""
+
+    def __init__(self, lookup, block_size: int, chunk: int, discard_partial_chunks: bool,
+                 save_decode_cache: bool = False, kv_role: str = "kv_both"):
+        self.lookup = lookup
+        self.block_size = block_size
+        self.chunk = chunk
+        self.discard_partial_chunks = discard_partial_chunks
+        self.save_decode_cache = save_decode_cache
+        self.kv_role = kv_role
+        self.load_specs: dict[str, LoadSpec] = {}
+        self.trackers: dict[str, RequestTracker] = {}
+        self.unfinished: dict[str, object] = {}
+        self.num_lookups = 0
+        self.num_hit_tokens = 0
+        self.num_requested_tokens = 0
+
+    # get_num_new_matched_tokens (adapter :1141-1228); side-effect free apart from the lease
+    def num_new_matched_tokens(self, req_id: str, prompt_token_ids, num_tokens: int,
+                               num_computed_tokens: int) -> int:
+        if self.kv_role == "kv_producer":
+            return 0
+        hit = int(self.lookup(prompt_token_ids))
+        self.num_lookups += 1
+        self.num_hit_tokens += hit
+        self.num_requested_tokens += len(prompt_token_ids)
+        need = hit - num_computed_tokens
+        if hit == num_tokens:
+            need -= 1  # full-prompt hit: vLLM must still compute the last token
+        self.load_specs[req_id] = LoadSpec(num_computed_tokens, hit, False)
+        return max(need, 0)
+
+    # update_state_after_alloc (adapter :1231-1293)
+    def after_alloc(self, request, num_external_tokens: int):
+        rid = request.request_id
+        self.unfinished[rid] = request
+        spec = self.load_specs.get(rid)
+        if spec is None:
+            return
+        spec.can_load = num_external_tokens > 0
+
+    # build_connector_meta (adapter :1296-1407)
+    def build_meta(self, scheduler_output) -> list[ReqMeta]:
+        out: list[ReqMeta] = []
+        force_skip = self.kv_role == "kv_consumer"
+        for rid in scheduler_output.finished_req_ids:
+            self.trackers.pop(rid, None)
+            self.unfinished.pop(rid, None)
+            self.load_specs.pop(rid, None)
+        for req in scheduler_output.scheduled_new_reqs:
+            spec = self.load_specs.pop(req.req_id, None)
+            n_compute = req.num_computed_tokens + scheduler_output.num_scheduled_tokens[req.req_id]
+            saved = spec.external_cached_tokens if spec is not None else 0
+            prompt = req.prompt_token_ids or []
+            tr = RequestTracker(req.req_id, len(prompt), list(prompt[:n_compute]),
+                                first_group(req.block_ids), num_saved_tokens=saved, skip_save=force_skip)
+            self.trackers[req.req_id] = tr
+            m = make_req_meta(tr, self.block_size, self.chunk, spec, self.discard_partial_chunks,
+                              self.save_decode_cache)
+            if m is not None:
+                out.append(m)
+        cached = scheduler_output.scheduled_cached_reqs
+        for i, rid in enumerate(cached.req_ids):
+            tr = self.trackers.get(rid)
+            if tr is None:
+                continue
+            n_new = scheduler_output.num_scheduled_tokens[rid]
+            req = self.unfinished.get(rid)
+            cur = len(tr.token_ids)
+            if req is not None:
+                new_tokens = list(req.all_token_ids[cur:cur + n_new])
+            elif rid in getattr(cached, "all_token_ids", {}):
+                new_tokens = list(cached.all_token_ids[rid][cur:cur + n_new])
+            else:
+                new_tokens = []
+            resumed = rid in getattr(cached, "resumed_req_ids", ())
+            tr.update(new_tokens, cached.new_block_ids[i], resumed)
+            m = make_req_meta(tr, self.block_size, self.chunk, None, self.discard_partial_chunks,
+                              self.save_decode_cache)
+            if m is not None:
+                out.append(m)
+        return out
+
+
+@dataclass
+class WorkerStats:
+    num_stored_tokens: int = 0
+    num_loaded_tokens: int = 0
+    num_load_shortfalls: int = 0
+    retrieve_seconds: float = 0.0
+    retrieve_calls: int = 0
+
+
+class WorkerState:
+    """Worker-role half: turns ReqMeta into engine.store / engine.retrieve calls."""
+
+    def __init__(self, engine, block_size: int, chunk: int, kv_role: str = "kv_both"):
+        self.engine = engine
+        self.block_size = block_size
+        self.chunk = chunk
+        self.kv_role = kv_role
+        self.load_error_blocks: set[int] = set()
+        self.pending_tickets: list[int] = []
+        self.stats = WorkerStats()
+
+    def start_load(self, metas: list[ReqMeta], stream=None):
+        """start_load_kv (adapter :798-905)."""
+        import time
+        for m in metas:
+            spec = m.load_spec
+            if spec is None or not spec.can_load:
+                continue
+            n = min(spec.external_cached_tokens, len(m.token_ids))
+            if n <= 0:
+                continue
+            tokens = m.token_ids[:n]
+            sm = m.slot_mapping(self.block_size)[:n]
+            mask = np.ones(n, dtype=bool)
+            masked = spec.vllm_cached_tokens // self.chunk * self.chunk
+            mask[:masked] = False
+            t0 = time.perf_counter()
+            ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
+            self.stats.retrieve_seconds += time.perf_counter() - t0
+            self.stats.retrieve_calls += 1
+            got = int(ret.sum())
+            self.stats.num_loaded_tokens += got
+            if masked + got < n:
+                # short load: report the blocks vLLM believes are filled so it recomputes them
+                # (KVConnectorBase_V1.get_block_ids_with_load_errors, base.py:375-393)
+                self.stats.num_load_shortfalls += 1
+                first_bad = (masked + got) // self.block_size
+                last = (n + self.block_size - 1) // self.block_size
+                self.load_error_blocks.update(m.block_ids[first_bad:last])
+
+    def save(self, metas: list[ReqMeta], stream=None):
+        """wait_for_save (adapter :1033-1128).  Blocks only until the gather kernels are queued;
+        the caller's stream is made to wait for them, the D2H runs behind."""
+        if self.kv_role == "kv_consumer":
+            return
+        for m in metas:
+            ss = m.save_spec
+            if ss is None or not ss.can_save:
+                continue
+            tokens = m.token_ids
+            n = len(tokens)
+            if not m.is_last_prefill:
+                n = n // self.chunk * self.chunk
+            lead = ss.skip_leading_tokens // self.chunk * self.chunk
+            if n <= lead:
+                continue
+            sm = m.slot_mapping(self.block_size)[:n]
+            mask = np.ones(n, dtype=bool)
+            mask[:lead] = False
+            ticket = self.engine.store(tokens[:n], mask, sm, offset=lead, stream=stream)
+            if ticket:
+                self.pending_tickets.append(ticket)
+            self.stats.num_stored_tokens += n - lead
+            ss.skip_leading_tokens = n
+
+    def reap(self):
+        self.pending_tickets = [t for t in self.pending_tickets if not self.engine.poll(t)]
+
+    def take_load_errors(self) -> set[int]:
+        e, self.load_error_blocks = self.load_error_blocks, set()
+        return e

@@ -157,7 +157,9 @@ struct b200kv_ctx {
 
   uint8_t* d_staging = nullptr;
   std::vector<StageSlot> stage;
-  uint32_t stage_next = 0;
+  // The ring is split in two halves — stores allocate from [0, n_store), loads from [n_store, n):
+  // a TTFT-critical load must never queue behind the D2H of an unrelated store.
+  uint32_t n_store_slots = 0, store_next = 0, load_next = 0;
 
   TableSlot tables[kTableSlots];
   uint32_t table_next = 0;
@@ -176,7 +178,7 @@ struct b200kv_ctx {
   b200kv_engine_stats stats{};
 
   // bulk-kernel launch shape
-  int S = 4, LAG = 2, ctas_per_sm = 1;
+  int S = 2, LAG = 1, ctas_per_sm = 1;  // swept on B200: profiles/sweep_r01.txt
   uint32_t piece_tokens = 0, pieces = 0, stage_bytes = 0;
 };
 
@@ -542,7 +544,7 @@ extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool
   ctx->sm_count = prop.multiProcessorCount;
 
   // launch shape of the bulk kernel
-  ctx->S = cfg->stages > 0 ? cfg->stages : env_int("B200KV_STAGES", 4);
+  ctx->S = cfg->stages > 0 ? cfg->stages : env_int("B200KV_STAGES", 2);
   ctx->LAG = env_int("B200KV_LAG", ctx->S / 2);
   ctx->ctas_per_sm = cfg->ctas_per_sm > 0 ? cfg->ctas_per_sm : env_int("B200KV_CTAS_PER_SM", 1);
   const uint32_t stage_max = static_cast<uint32_t>(env_int("B200KV_STAGE_KB", 32)) << 10;
@@ -566,6 +568,8 @@ extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool
     CU_TRY(cudaMalloc(&ctx->d_staging, n_stage * g.chunk_bytes));
     ctx->stage.resize(n_stage);
     for (auto& s : ctx->stage) CU_TRY(cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+    if (pool && n_stage < 2) return B200KV_EINVAL;  // one half each for stores and loads
+    ctx->n_store_slots = static_cast<uint32_t>(n_stage / 2);
   } else if (pool) {
     return B200KV_EINVAL;  // store/load need at least one staging chunk
   }
@@ -765,7 +769,7 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
   CU_TRY(cudaEventDestroy(ev_compute));
 
   timing_reset(ctx, 0);
-  const size_t n_stage = ctx->stage.size();
+  const size_t n_stage = ctx->n_store_slots;
   for (size_t b0 = 0; b0 < todo.size(); b0 += n_stage) {
     const size_t nb = std::min(n_stage, todo.size() - b0);
     std::vector<Run> runs;
@@ -780,8 +784,8 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       // dense op-relative token index: chunk i of this batch starts at i*C
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs);
       if (rc) return rc;
-      sidx[i] = ctx->stage_next;
-      ctx->stage_next = (ctx->stage_next + 1) % static_cast<uint32_t>(n_stage);
+      sidx[i] = ctx->store_next;
+      ctx->store_next = (ctx->store_next + 1) % static_cast<uint32_t>(n_stage);
       addrs[i] = reinterpret_cast<uint64_t>(ctx->d_staging) + static_cast<uint64_t>(sidx[i]) * g.chunk_bytes;
       if (ctx->stage[sidx[i]].used) CU_TRY(cudaStreamWaitEvent(ctx->s_gather, ctx->stage[sidx[i]].free_ev, 0));
       batch_tokens = static_cast<uint32_t>(i) * g.C + t.n_tok;
@@ -879,7 +883,7 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
   CU_TRY(cudaEventDestroy(ev_compute));
 
   timing_reset(ctx, 1);
-  const size_t n_stage = ctx->stage.size();
+  const size_t n_stage = ctx->stage.size() - ctx->n_store_slots;
   int64_t loaded = 0;
   for (size_t b0 = 0; b0 < todo.size(); b0 += n_stage) {
     const size_t nb = std::min(n_stage, todo.size() - b0);
@@ -893,8 +897,8 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs);
       if (rc) return rc;
-      sidx[i] = ctx->stage_next;
-      ctx->stage_next = (ctx->stage_next + 1) % static_cast<uint32_t>(n_stage);
+      sidx[i] = ctx->n_store_slots + ctx->load_next;
+      ctx->load_next = (ctx->load_next + 1) % static_cast<uint32_t>(n_stage);
       addrs[i] = reinterpret_cast<uint64_t>(ctx->d_staging) + static_cast<uint64_t>(sidx[i]) * g.chunk_bytes;
     }
     offs[nb] = static_cast<uint32_t>(runs.size());

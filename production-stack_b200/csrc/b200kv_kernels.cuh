@@ -343,9 +343,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
-    uint32_t total = 0;
+  }
+  __syncthreads();  // barrier initialised before any lane can signal it
+  if (threadIdx.x < 32) {
+    // warp 0 walks the chunk's run list in parallel (one run per lane): the table reads are one
+    // L2 round trip instead of a serial chain, and every lane issues its own bulk copy.
+    uint32_t mine = 0;
     const uint32_t r0 = p.chunk_run_off[c], r1 = p.chunk_run_off[c + 1];
-    for (uint32_t r = r0; r < r1; ++r) {
+    for (uint32_t r = r0 + threadIdx.x; r < r1; r += 32) {
       const Run run = p.runs[r];
       const int32_t lo = max(run.b, static_cast<int32_t>(win_lo));
       const int32_t hi = min(run.b + run.n, static_cast<int32_t>(win_lo + n_valid));
@@ -355,11 +360,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
                reinterpret_cast<const void*>(
                    paged_addr(p.paged, plane, static_cast<uint32_t>(run.a + (lo - run.b)))),
                bytes, &bar);
-      total += bytes;
+      mine += bytes;
     }
-    mbar_arrive_expect_tx(&bar, total);
+    const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
+    // complete_tx may land before this expect_tx: the phase cannot complete until the arrive
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, total);
   }
-  __syncthreads();  // barrier init + s_absmax zero visible
   mbar_wait(&bar, 0);
 
   // ---- per-head absmax over this CTA's tokens: a thread's 16-byte column has a fixed head ----
@@ -401,10 +407,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
   uint8_t* out = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
                                             static_cast<uint64_t>(rank * W) * (tb >> 1));
   const uint32_t nvec = n_valid * vpt;
-  for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
-    const uint32_t col = i % vpt;
-    const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(i) * 16);
-    st_na_v2(out + static_cast<size_t>(i) * 8, quant8(v, s_inv[(col * 16) / p.head_bytes]));
+  if ((kFp8Threads % vpt) == 0) {
+    // i % vpt == threadIdx.x % vpt for every i of this thread: one head, one scale, no division
+    const float inv = s_inv[((threadIdx.x % vpt) * 16) / p.head_bytes];
+    for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+      const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(i) * 16);
+      st_na_v2(out + static_cast<size_t>(i) * 8, quant8(v, inv));
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+      const uint32_t col = i % vpt;
+      const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(i) * 16);
+      st_na_v2(out + static_cast<size_t>(i) * 8, quant8(v, s_inv[(col * 16) / p.head_bytes]));
+    }
   }
   cluster_sync_all();  // keep smem alive until every peer CTA has read our s_absmax
 }
@@ -476,10 +491,18 @@ __global__ void __launch_bounds__(kFp8Threads) kv_fp8_load_kernel(const Fp8LoadP
     uint8_t* dst = reinterpret_cast<uint8_t*>(paged_addr(p.paged, plane, static_cast<uint32_t>(run.a)));
     const uint32_t vpt = tb >> 4;
     const uint32_t nvec = static_cast<uint32_t>(run.n) * vpt;
-    for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
-      const uint32_t col = i % vpt;
-      const uint2 q = *reinterpret_cast<const uint2*>(smem + static_cast<size_t>(i) * 8);
-      st_na_v4(dst + static_cast<size_t>(i) * 16, dequant8(q, s_scale[(col * 16) / p.head_bytes]));
+    if ((kFp8Threads % vpt) == 0) {
+      const float sc = s_scale[((threadIdx.x % vpt) * 16) / p.head_bytes];
+      for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+        const uint2 q = *reinterpret_cast<const uint2*>(smem + static_cast<size_t>(i) * 8);
+        st_na_v4(dst + static_cast<size_t>(i) * 16, dequant8(q, sc));
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+        const uint32_t col = i % vpt;
+        const uint2 q = *reinterpret_cast<const uint2*>(smem + static_cast<size_t>(i) * 8);
+        st_na_v4(dst + static_cast<size_t>(i) * 16, dequant8(q, s_scale[(col * 16) / p.head_bytes]));
+      }
     }
     __syncthreads();  // smem + s_scale reusable
   }

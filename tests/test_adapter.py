@@ -1,0 +1,171 @@
+"""Scheduler/worker state machine of the connector against fake SchedulerOutputs (CPU).
+The worker half is driven with an engine stand-in that forwards to the oracle engine, so the
+end-to-end request flow (lookup -> alloc -> load -> save) is checked token for token."""
+from types import SimpleNamespace as NS
+
+import numpy as np
+
+from b200kv.adapter import (LoadSpec, ReqMeta, RequestTracker, SchedulerState, WorkerState, first_group,
+                            make_req_meta)
+from oracle import kv_oracle as ko
+
+BS, C = 16, 64
+
+
+class OracleBackedEngine:
+    """Test stand-in with KVEngine's call signatures, backed by oracle.OracleEngine."""
+
+    def __init__(self, layers):
+        self.oe = ko.OracleEngine(C)
+        self.layers = layers
+        self.calls = []
+
+    def store(self, tokens, mask, slot_mapping, offset=0, stream=None):
+        self.calls.append(("store", len(tokens), offset))
+        self.oe.store(tokens, mask, self.layers, slot_mapping, offset)
+        return 1
+
+    def retrieve(self, tokens, mask, slot_mapping, stream=None):
+        self.calls.append(("retrieve", len(tokens), int((~mask).sum())))
+        return self.oe.retrieve(tokens, mask, self.layers, slot_mapping)
+
+    def poll(self, t):
+        return True
+
+
+def sched_out(new=(), cached=None, num_sched=None, finished=()):
+    cached = cached or NS(req_ids=[], new_block_ids=[], resumed_req_ids=set(), all_token_ids={})
+    return NS(scheduled_new_reqs=list(new), scheduled_cached_reqs=cached,
+              num_scheduled_tokens=num_sched or {}, finished_req_ids=set(finished))
+
+
+def new_req(rid, prompt, blocks, computed=0):
+    return NS(req_id=rid, prompt_token_ids=list(prompt), block_ids=(list(blocks),), num_computed_tokens=computed)
+
+
+def test_first_group_shapes():
+    assert first_group(([1, 2], [9])) == [1, 2]
+    assert first_group([3, 4]) == [3, 4]
+    assert first_group(None) == [] and first_group(()) == []
+
+
+def test_save_planning_matches_oracle_plan_save():
+    for prompt_len, n_in, saved, discard, decode in [
+        (600, 600, 0, False, False), (600, 600, 0, True, False), (900, 600, 0, False, False),
+        (900, 700, 512, False, False), (900, 900, 512, False, False), (900, 901, 900, False, True),
+        (64, 64, 0, False, False), (10, 10, 0, False, False), (10, 10, 0, True, False)]:
+        tr = RequestTracker("r", prompt_len, list(range(n_in)), list(range(100)), num_saved_tokens=saved,
+                            is_decode_phase=decode)
+        m = make_req_meta(tr, BS, 256, None, discard)
+        want = ko.plan_save(n_in, prompt_len, saved, 256, discard, decode)
+        if want is None:
+            assert m is None or not m.save_spec.can_save or m.save_spec.skip_leading_tokens // 256 * 256 >= len(m.token_ids)
+        else:
+            lead, n_save = want
+            assert m is not None and m.save_spec.can_save
+            assert m.save_spec.skip_leading_tokens // 256 * 256 == lead and len(m.token_ids) == n_save
+
+
+def test_request_flow_miss_then_hit_with_last_token_rule():
+    rng = np.random.default_rng(0)
+    layers = [rng.integers(0, 2 ** 16, (2, 64, BS, 2, 8), dtype=np.uint16) for _ in range(2)]
+    eng = OracleBackedEngine(layers)
+    lookup = lambda toks: eng.oe.lookup(toks)
+    sched = SchedulerState(lookup, BS, C, discard_partial_chunks=False)
+    worker = WorkerState(eng, BS, C)
+    prompt = list(rng.integers(0, 1000, 3 * C + 10))           # 202 tokens
+    blocks = list(range(10, 10 + 13))
+    # --- turn 1: nothing cached ---------------------------------------------------------------
+    req = NS(request_id="a", prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt)
+    assert sched.num_new_matched_tokens("a", prompt, len(prompt), 0) == 0
+    sched.after_alloc(req, 0)
+    metas = sched.build_meta(sched_out([new_req("a", prompt, blocks)], num_sched={"a": len(prompt)}))
+    assert len(metas) == 1 and metas[0].is_last_prefill and metas[0].load_spec is None
+    worker.start_load(metas)
+    worker.save(metas)
+    assert eng.calls == [("store", len(prompt), 0)]
+    assert eng.oe.lookup(prompt) == len(prompt)                 # partial tail chunk saved too
+    # decode steps never save (adapter :313-318)
+    cached = NS(req_ids=["a"], new_block_ids=[None], resumed_req_ids=set(), all_token_ids={})
+    req.all_token_ids = prompt + [5]
+    assert sched.build_meta(sched_out(cached=cached, num_sched={"a": 1})) == []
+    sched.build_meta(sched_out(finished=["a"]))
+    assert "a" not in sched.trackers
+    # --- turn 2: same prompt -> full hit, last token recomputed (adapter :1205-1209) ------------
+    req2 = NS(request_id="b", prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt)
+    need = sched.num_new_matched_tokens("b", prompt, len(prompt), 0)
+    assert need == len(prompt) - 1
+    sched.after_alloc(req2, need)
+    blocks2 = list(range(40, 53))
+    metas = sched.build_meta(sched_out([new_req("b", prompt, blocks2, computed=need)], num_sched={"b": 1}))
+    m = metas[0]
+    assert m.load_spec is not None and m.load_spec.can_load and m.load_spec.external_cached_tokens == len(prompt)
+    eng.calls.clear()
+    before = [l.copy() for l in layers]
+    worker.start_load(metas)
+    assert eng.calls == [("retrieve", len(prompt), 0)]
+    sm_src = ko.slot_mapping_from_blocks(blocks, BS, len(prompt))
+    sm_dst = ko.slot_mapping_from_blocks(blocks2, BS, len(prompt))
+    assert np.array_equal(ko.gather_tokens(layers, sm_dst), ko.gather_tokens(before, sm_src))
+    worker.save(metas)                                          # everything already saved -> no store
+    assert [c for c in eng.calls if c[0] == "store"] == []
+    assert worker.take_load_errors() == set()
+    # --- turn 3: longer prompt sharing 2 chunks, vLLM prefix cache already holds 1 chunk ---------
+    prompt3 = prompt[: 2 * C] + list(rng.integers(1000, 2000, 100))
+    need3 = sched.num_new_matched_tokens("c", prompt3, len(prompt3), C)
+    assert need3 == C                                           # 2 chunks hit - 1 chunk computed
+    req3 = NS(request_id="c", prompt_token_ids=prompt3, num_tokens=len(prompt3), all_token_ids=prompt3)
+    sched.after_alloc(req3, need3)
+    metas = sched.build_meta(sched_out([new_req("c", prompt3, list(range(20, 35)), computed=2 * C)],
+                                       num_sched={"c": len(prompt3) - 2 * C}))
+    eng.calls.clear()
+    worker.start_load(metas)
+    assert eng.calls == [("retrieve", 2 * C, C)]                # first chunk masked (vLLM has it)
+    worker.save(metas)
+    assert eng.calls[-1] == ("store", len(prompt3), 2 * C)      # only the new tail is stored
+    assert sched.num_lookups == 3 and sched.num_hit_tokens == len(prompt) + 2 * C
+
+
+def test_short_load_reports_error_blocks():
+    class ShortEngine(OracleBackedEngine):
+        def retrieve(self, tokens, mask, slot_mapping, stream=None):
+            r = np.zeros(len(tokens), bool)
+            r[:C] = True                                        # only the first chunk arrives
+            return r
+
+    eng = ShortEngine([np.zeros((2, 8, BS, 1, 8), np.uint16)])
+    w = WorkerState(eng, BS, C)
+    m = ReqMeta("x", np.arange(3 * C, dtype=np.int32), list(range(100, 112)), load_spec=LoadSpec(0, 3 * C, True))
+    w.start_load([m])
+    assert w.take_load_errors() == set(range(100 + C // BS, 112))
+    assert w.take_load_errors() == set()
+
+
+def test_consumer_never_saves_and_producer_never_looks_up():
+    sched = SchedulerState(lambda t: 128, BS, C, False, kv_role="kv_producer")
+    assert sched.num_new_matched_tokens("p", list(range(200)), 200, 0) == 0
+    eng = OracleBackedEngine([np.zeros((2, 8, BS, 1, 8), np.uint16)])
+    w = WorkerState(eng, BS, C, kv_role="kv_consumer")
+    from b200kv.adapter import SaveSpec
+    w.save([ReqMeta("x", np.arange(C, dtype=np.int32), [0, 1, 2, 3], True, SaveSpec(0, True))])
+    assert eng.calls == []
+
+
+def test_chunked_prefill_saves_whole_chunks_incrementally():
+    eng = OracleBackedEngine([np.zeros((2, 64, BS, 1, 8), np.uint16)])
+    sched = SchedulerState(lambda t: 0, BS, C, False)
+    w = WorkerState(eng, BS, C)
+    prompt = list(range(1, 3 * C + 21))                         # 212 tokens, prefill in 100-token steps
+    req = NS(request_id="q", prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt)
+    sched.num_new_matched_tokens("q", prompt, len(prompt), 0)
+    sched.after_alloc(req, 0)
+    w.save(sched.build_meta(sched_out([new_req("q", prompt, list(range(7)))], num_sched={"q": 100})))
+    assert eng.calls == [("store", C, 0)]                       # 100 tokens -> one whole chunk
+    cached = NS(req_ids=["q"], new_block_ids=[(list(range(7, 14)),)], resumed_req_ids=set(), all_token_ids={})
+    w.save(sched.build_meta(sched_out(cached=cached, num_sched={"q": 100})))
+    assert eng.calls[-1] == ("store", 3 * C, C)                 # 200 tokens -> chunks 1,2 new
+    cached = NS(req_ids=["q"], new_block_ids=[None], resumed_req_ids=set(), all_token_ids={})
+    w.save(sched.build_meta(sched_out(cached=cached, num_sched={"q": 12})))
+    # reference rule (adapter :313-316): once something is saved, a step that does not reach the
+    # next chunk boundary saves nothing — even the last prefill's partial tail
+    assert len(eng.calls) == 2

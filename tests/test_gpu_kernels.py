@@ -357,3 +357,34 @@ def test_full_size_llama3_8b_round_trip_properties(fmt):
         assert torch.equal(b1, b2)
     eng.close()
     pool.close()
+
+
+@pytest.mark.parametrize("n_tok", [40, 256, 1000])
+def test_fp8_store_token_granular_and_block_mappings(n_tok):
+    """FP8 store with a token-granular mapping (40 single-token runs, walked by warp 0 in
+    parallel) and block-structured ones: the oracle's codes and scales, bit for bit."""
+    need_gpu()
+    p = SMALL
+    rng = np.random.default_rng(77 + n_tok)
+    host = mk_host_layers(rng, p["L"], p["NB"], p["bs"], p["H"], p["D"])
+    dev = to_dev(host)
+    geom = KVGeometry(p["L"], p["H"], p["D"], p["NB"], p["bs"], p["C"], 2, 0, FMT_FP8)
+    eng = KVEngine(geom, None, 0, staging_bytes=0)
+    eng.register_kv_caches(dev)
+    sm = rng.permutation(p["NB"] * p["bs"])[:n_tok].astype(np.int64) if n_tok == 40 else \
+        ko.slot_mapping_from_blocks(rng.permutation(p["NB"])[: (n_tok + 15) // 16], 16, n_tok)
+    n_chunks = (n_tok + p["C"] - 1) // p["C"]
+    buf = torch.zeros(n_chunks * geom.chunk_bytes, dtype=torch.uint8, device="cuda:0")
+    eng.gather(sm, buf.data_ptr())
+    torch.cuda.synchronize()
+    want, cb, so = oracle_c.gather(host, sm, p["C"], "fp8")
+    got = buf.cpu().numpy()
+    tb = geom.token_bytes // 2
+    for c in range(n_chunks):
+        n = min(p["C"], n_tok - c * p["C"])
+        for plane in range(2 * p["L"]):
+            o = c * cb + plane * p["C"] * tb
+            assert np.array_equal(got[o:o + n * tb], want[o:o + n * tb]), (c, plane)
+        s = c * cb + so
+        assert np.array_equal(got[s:s + 2 * p["L"] * p["H"] * 4], want[s:s + 2 * p["L"] * p["H"] * 4])
+    eng.close()

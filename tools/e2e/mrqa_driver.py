@@ -1,0 +1,148 @@
+"""Multi-round-QA workload driver — a restatement (not a copy) of the reference harness
+benchmarks/multi-round-qa/multi-round-qa.py for the GPU box, where /root/reference does not exist.
+Where the reference tree is available (this build container) the unmodified harness is what
+tests/test_router_plumbing.py drives; this driver produces the same traffic shape:
+
+* first turn = "Hi, here's some system prompt: " + "hi "*S + "For user <id>, here are some other
+  context: " + "hi "*U + question            (multi-round-qa.py:232-251)
+* each later turn appends the previous answer and "Here's question #k: can you tell me a new long
+  story with a happy ending?"                 (:246-251, :293-301)
+* requests are /v1/chat/completions, stream=True, temperature 0, max_tokens = answer_len, header
+  x-user-id: <id>                             (:126-140, :288)
+* per-user gap = num_users / qps seconds; users join every gap*(rounds-1)/num_users s (:367-372)
+* TTFT = time to the first non-empty streamed delta (:143-171); output = per-request rows
+  (prompt_tokens, generation_tokens, ttft, generation_time, user_id, question_id, launch, finish)
+  (:346-356) + the p50/mean TTFT and output tokens/s summary (:493-526).
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import json
+import statistics
+import time
+
+import aiohttp
+
+
+def system_prompt(uid: int, S: int, U: int) -> str:
+    return (f"Hi, here's some system prompt: {' '.join(['hi'] * S)}."
+            f"For user {uid}, here are some other context: {' '.join(['hi'] * U)}.")
+
+
+def question(k: int) -> str:
+    return f"Here's question #{k}: can you tell me a new long story with a happy ending?"
+
+
+async def one_request(session, base_url, model, messages, max_tokens, uid):
+    t0 = time.time()
+    first = None
+    text = []
+    usage = {}
+    body = {"model": model, "messages": messages, "temperature": 0, "stream": True, "max_tokens": max_tokens,
+            "stream_options": {"include_usage": True}}
+    async with session.post(base_url + "/chat/completions", json=body, headers={"x-user-id": str(uid)}) as r:
+        r.raise_for_status()
+        async for raw in r.content:
+            line = raw.decode().strip()
+            if not line.startswith("data:"):
+                continue
+            data = line[5:].strip()
+            if data == "[DONE]":
+                break
+            obj = json.loads(data)
+            if obj.get("usage"):
+                usage = obj["usage"]
+            ch = obj.get("choices") or []
+            if not ch:
+                continue
+            delta = ch[0].get("delta", {})
+            piece = delta.get("content") or delta.get("reasoning_content")
+            if piece:
+                if first is None:
+                    first = time.time()
+                text.append(piece)
+    t1 = time.time()
+    first = first if first is not None else t0
+    return {"body": "".join(text), "ttft": first - t0, "generation_time": t1 - first,
+            "prompt_tokens": usage.get("prompt_tokens", 0), "generation_tokens": usage.get("completion_tokens", 0),
+            "launch_time": t0, "finish_time": t1}
+
+
+async def user_session(session, args, uid, start_delay, rows):
+    await asyncio.sleep(start_delay)
+    gap = args.num_users / args.qps
+    history = []
+    for k in range(1, args.num_rounds + 1):
+        t_launch = time.time()
+        prompt = question(k)
+        if not history:
+            prompt = system_prompt(uid, args.shared_system_prompt, args.user_history_prompt) + prompt
+        history.append({"role": "user", "content": prompt})
+        try:
+            res = await one_request(session, args.base_url, args.model, history, args.answer_len, uid)
+        except Exception as e:  # a failed request is recorded, not fatal (the harness logs and goes on)
+            rows.append({"user_id": uid, "question_id": k, "error": repr(e)})
+            return
+        history.append({"role": "assistant", "content": res.pop("body")})
+        res.update(user_id=uid, question_id=k)
+        rows.append(res)
+        wait = gap - (time.time() - t_launch)
+        if wait > 0 and k < args.num_rounds:
+            await asyncio.sleep(wait)
+
+
+async def run(args):
+    rows = []
+    gap = args.num_users / args.qps
+    join_gap = gap * (args.num_rounds - 1) / args.num_users if args.num_rounds > 1 else 0
+    timeout = aiohttp.ClientTimeout(total=None)
+    async with aiohttp.ClientSession(timeout=timeout) as session:
+        t0 = time.time()
+        await asyncio.gather(*[user_session(session, args, args.init_user_id + i + 1, i * join_gap, rows)
+                               for i in range(args.num_users)])
+        t1 = time.time()
+    ok = [r for r in rows if "error" not in r]
+    ttfts = sorted(r["ttft"] for r in ok)
+    later = sorted(r["ttft"] for r in ok if r["question_id"] > 1)
+    first = sorted(r["ttft"] for r in ok if r["question_id"] == 1)
+    gen = sum(r["generation_tokens"] for r in ok)
+    summary = {
+        "requests": len(rows), "failed": len(rows) - len(ok), "wall_s": t1 - t0,
+        "ttft_p50_s": statistics.median(ttfts) if ttfts else None,
+        "ttft_mean_s": statistics.fmean(ttfts) if ttfts else None,
+        "ttft_p50_first_turn_s": statistics.median(first) if first else None,
+        "ttft_p50_later_turns_s": statistics.median(later) if later else None,
+        "ttft_p90_s": ttfts[int(0.9 * (len(ttfts) - 1))] if ttfts else None,
+        "output_tokens_per_s": gen / (t1 - t0) if t1 > t0 else None,
+        "input_tokens_per_s": sum(r["prompt_tokens"] for r in ok) / (t1 - t0) if t1 > t0 else None,
+        "mean_prompt_tokens": statistics.fmean(r["prompt_tokens"] for r in ok) if ok else None,
+        "config": {k: getattr(args, k) for k in ("num_users", "num_rounds", "qps", "shared_system_prompt",
+                                                 "user_history_prompt", "answer_len", "model")},
+    }
+    return rows, summary
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--base-url", default="http://127.0.0.1:8000/v1")
+    ap.add_argument("--model", required=True)
+    ap.add_argument("--num-users", type=int, default=16)
+    ap.add_argument("--num-rounds", type=int, default=4)
+    ap.add_argument("--qps", type=float, default=2.0)
+    ap.add_argument("--shared-system-prompt", type=int, default=512)
+    ap.add_argument("--user-history-prompt", type=int, default=1536)
+    ap.add_argument("--answer-len", type=int, default=64)
+    ap.add_argument("--init-user-id", type=int, default=0)
+    ap.add_argument("--output", default=None, help="per-request rows as JSON lines")
+    args = ap.parse_args()
+    rows, summary = asyncio.run(run(args))
+    if args.output:
+        with open(args.output, "w") as f:
+            for r in rows:
+                f.write(json.dumps(r) + "\n")
+    print(json.dumps(summary))
+
+
+if __name__ == "__main__":
+    main()
