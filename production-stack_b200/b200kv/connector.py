@@ -24,7 +24,7 @@ from vllm.distributed.kv_transfer.kv_connector.v1.base import (KVConnectorBase_V
 from . import _lib
 from .adapter import ReqMeta, SchedulerState, WorkerState
 from .config import B200KVConfig
-from .engine import KVEngine, KVGeometry, KVPool, paged_layout_of
+from .engine import KVEngine, KVGeometry, KVPool, paged_layout_of, xxh64
 
 if TYPE_CHECKING:
     from vllm.config import VllmConfig
@@ -54,6 +54,11 @@ def geometry_from_vllm(vllm_config, cfg: B200KVConfig, n_blocks: int = 1) -> KVG
     return KVGeometry(n_layers=mc.get_num_layers(pc), n_kv_heads=mc.get_num_kv_heads(pc),
                       head_dim=mc.get_head_size(), n_blocks=n_blocks, block_tokens=cc.block_size,
                       chunk_tokens=cfg.chunk_size, elem_bytes=elem, block_stride_bytes=0, fmt=cfg.fmt)
+
+
+def owner_tag_of(instance_id: str) -> int:
+    """Stable 31-bit tag of LMCACHE_LMCACHE_INSTANCE_ID (not Python's salted hash())."""
+    return (xxh64(instance_id.encode(), 0) & 0x7FFFFFFF) or 1
 
 
 def pool_name_for(vllm_config, cfg: B200KVConfig) -> str:
@@ -87,6 +92,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._engine: KVEngine | None = None
         self._worker: WorkerState | None = None
         self._sched: SchedulerState | None = None
+        self._controller = None
         if role == KVConnectorRole.SCHEDULER:
             seed = geom.key_seed(self._model, self._world, 0)
             lease = self.cfg.lookup_lease_ms
@@ -126,10 +132,16 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                              f"({geom.chunk_bytes} vs {geom0.chunk_bytes} bytes per chunk)")
         rank = getattr(self._vllm_config.parallel_config, "rank", 0)
         self._engine = KVEngine(geom, self._pool, device=t0.device.index or 0,
-                                staging_bytes=self.cfg.staging_mb << 20, owner=abs(hash(self.cfg.instance_id)) & 0x7FFFFFFF,
+                                staging_bytes=self.cfg.staging_mb << 20, owner=owner_tag_of(self.cfg.instance_id),
                                 variant=self.cfg.variant, key_seed=geom0.key_seed(self._model, self._world, rank))
         self._engine.register_kv_caches(tensors)
         self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role)
+        if self.cfg.enable_controller and self.cfg.controller_pull_url and rank == 0:
+            from .controller_client import ControllerClient
+            self._controller = ControllerClient(
+                self.cfg.controller_pull_url, self.cfg.instance_id, self._pool_name, self._engine.key_seed,
+                self._chunk, owner_tag=owner_tag_of(self.cfg.instance_id) if self.cfg.pool_name else 0,
+                include_partial=not self._discard_partial, heartbeat_s=self.cfg.worker_heartbeat_s)
         logger.info("b200kv registered %d layers, %d blocks, stride %d", len(tensors), nb, stride)
 
     def _metas(self) -> list[ReqMeta]:
@@ -162,6 +174,9 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         return self._worker.take_load_errors() if self._worker is not None else set()
 
     def shutdown(self):
+        if self._controller is not None:
+            self._controller.close()
+            self._controller = None
         if self._engine is not None:
             self._engine.wait_all()
             self._engine.close()

@@ -1,0 +1,108 @@
+"""Plugin-slot checks that need no GPU: vLLM's own factory resolves the connector by module path,
+HMA support is advertised, the scheduler role works against the shm index, the config surface
+honours the reference's env names, and the `lmcache`-named alias resolves (chart-level drop-in)."""
+import os
+import sys
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+
+vllm = pytest.importorskip("vllm")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fake_vllm_config(engine_id, extra=None, role="kv_both"):
+    import torch
+    from vllm.config import KVTransferConfig
+    ktc = KVTransferConfig(kv_connector="B200KVConnector", kv_connector_module_path="b200kv.connector",
+                           kv_role=role, engine_id=engine_id, kv_connector_extra_config=extra or {})
+    mc = NS(model="synth-llama", dtype=torch.bfloat16, get_num_layers=lambda pc: 4, get_num_kv_heads=lambda pc: 2,
+            get_head_size=lambda: 64)
+    return NS(kv_transfer_config=ktc, model_config=mc, parallel_config=NS(tensor_parallel_size=1, rank=0),
+              cache_config=NS(block_size=16, cache_dtype="auto"),
+              scheduler_config=NS(disable_hybrid_kv_cache_manager=False))
+
+
+def test_factory_resolves_class_and_hma():
+    from vllm.distributed.kv_transfer.kv_connector.factory import KVConnectorFactory
+    from vllm.distributed.kv_transfer.kv_connector.v1.base import supports_hma
+    cfg = fake_vllm_config("abi")
+    cls = KVConnectorFactory.get_connector_class(cfg.kv_transfer_config)
+    from b200kv.connector import B200KVConnector
+    assert cls is B200KVConnector and supports_hma(cls)
+    assert cls.get_required_kvcache_layout(cfg) == "NHD"
+
+
+def test_scheduler_role_lookup_and_metadata(monkeypatch):
+    from vllm.distributed.kv_transfer.kv_connector.v1.base import KVConnectorRole
+
+    from b200kv import KVPool, chunk_keys
+    from b200kv.connector import B200KVConnector, B200KVConnectorMetadata, geometry_from_vllm
+    monkeypatch.setenv("LMCACHE_MAX_LOCAL_CPU_SIZE", "0.05")
+    monkeypatch.setenv("LMCACHE_CHUNK_SIZE", "64")
+    eid = f"t{os.getpid()}x{os.urandom(3).hex()}"
+    cfg = fake_vllm_config(eid)
+    conn = B200KVConnector(cfg, KVConnectorRole.SCHEDULER, None)
+    try:
+        geom = geometry_from_vllm(cfg, conn.cfg)
+        assert geom.chunk_tokens == 64 and geom.chunk_bytes == 4 * 2 * 64 * 2 * 64 * 2
+        prompt = list(range(200))
+        req = NS(request_id="r1", prompt_token_ids=prompt, num_tokens=200, all_token_ids=prompt)
+        assert conn.get_num_new_matched_tokens(req, 0) == (0, False)
+        # a worker (here: the test) commits the first two chunks into the shared index
+        seed = geom.key_seed("synth-llama", 1, 0)
+        keys = chunk_keys(np.asarray(prompt, np.int32), 64, seed)
+        for k in keys[:2]:
+            conn._pool.reserve(int(k), 64, 0, 0)
+            conn._pool.commit(int(k))
+        assert conn.get_num_new_matched_tokens(req, 0) == (128, False)
+        assert conn.get_num_new_matched_tokens(req, 64) == (64, False)
+        conn.update_state_after_alloc(req, None, 64)
+        so = NS(scheduled_new_reqs=[NS(req_id="r1", prompt_token_ids=prompt, block_ids=(list(range(13)),),
+                                       num_computed_tokens=128)],
+                scheduled_cached_reqs=NS(req_ids=[], new_block_ids=[], resumed_req_ids=set(), all_token_ids={}),
+                num_scheduled_tokens={"r1": 72}, finished_req_ids=set())
+        meta = conn.build_connector_meta(so)
+        assert isinstance(meta, B200KVConnectorMetadata) and len(meta.requests) == 1
+        m = meta.requests[0]
+        assert m.load_spec.can_load and m.load_spec.external_cached_tokens == 128 and m.load_spec.vllm_cached_tokens == 64
+        import pickle
+        assert pickle.loads(pickle.dumps(meta)).requests[0].block_ids == list(range(13))   # crosses processes
+        assert conn.request_finished(req, []) == (False, None)
+        assert conn.request_finished_all_groups(req, ([],)) == (False, None)
+    finally:
+        conn.shutdown()
+        KVPool.unlink("/b200kv-" + eid)
+
+
+def test_config_surface_uses_reference_env_names():
+    from b200kv.config import B200KVConfig
+    from b200kv import FMT_FP8, FMT_RAW
+    env = {"LMCACHE_CHUNK_SIZE": "128", "LMCACHE_LOCAL_CPU": "True", "LMCACHE_MAX_LOCAL_CPU_SIZE": "60",
+           "LMCACHE_REMOTE_SERDE": "cachegen", "LMCACHE_LMCACHE_INSTANCE_ID": "pod-7", "LMCACHE_ENABLE_CONTROLLER": "True",
+           "LMCACHE_CONTROLLER_PULL_URL": "router:9000", "LMCACHE_LMCACHE_WORKER_HEARTBEAT_TIME": "3",
+           "LMCACHE_MAX_LOCAL_DISK_SIZE": "10", "LMCACHE_USE_EXPERIMENTAL": "True"}
+    c = B200KVConfig.from_env(env)
+    assert (c.chunk_size, c.max_local_cpu_size_gb, c.fmt, c.instance_id) == (128, 60.0, FMT_FP8, "pod-7")
+    assert c.enable_controller and c.controller_pull_url == "router:9000" and c.worker_heartbeat_s == 3.0
+    assert c.pool_bytes == 60 << 30
+    c2 = B200KVConfig.from_env({}).apply_extra({"b200kv.format": "fp8", "lmcache.chunk_size": 512, "unrelated": 1})
+    assert c2.fmt == FMT_FP8 and c2.chunk_size == 512
+    assert B200KVConfig.from_env({"LMCACHE_REMOTE_SERDE": "naive"}).fmt == FMT_RAW
+    with pytest.raises(ValueError):
+        B200KVConfig.from_env({"B200KV_FORMAT": "int4"})
+
+
+def test_lmcache_named_alias_resolves():
+    sys.path.insert(0, os.path.join(ROOT, "production-stack_b200", "compat"))
+    try:
+        from lmcache.integration.vllm.vllm_v1_adapter import LMCacheConnectorV1Impl
+        import inspect
+        assert list(inspect.signature(LMCacheConnectorV1Impl.__init__).parameters)[1:] == ["vllm_config", "role", "parent"]
+        for name in ("register_kv_caches", "start_load_kv", "wait_for_layer_load", "save_kv_layer", "wait_for_save",
+                     "get_finished", "get_block_ids_with_load_errors", "get_kv_events", "get_num_new_matched_tokens",
+                     "update_state_after_alloc", "build_connector_meta", "request_finished"):
+            assert callable(getattr(LMCacheConnectorV1Impl, name))   # what lmcache_connector.py:120-354 forwards
+    finally:
+        sys.path.pop(0)
