@@ -58,6 +58,16 @@ extern "C" {
 #define B200KV_FMT_RAW 0
 #define B200KV_FMT_FP8 1
 
+/* ---- order inside one (block, K|V) tile of the paged cache ------------------------------ */
+/* NHD: [block_tokens][H][D] (FlashAttention default, vllm/v1/attention/backends/flash_attn.py:
+ *      152-170).  HND: [H][block_tokens][D] — what vLLM's FlashInfer/TRT-LLM backend REQUIRES on
+ *      Blackwell (vllm/v1/attention/selector.py:124-133 overrides the connector's wish), i.e. the
+ *      layout actually met on a B200.  Whole-block runs move as one contiguous tile in both; a
+ *      chunk stores tiles verbatim, so chunks of the two layouts never mix (the layout is part
+ *      of the key namespace).  FP8 requires NHD in this round.                               */
+#define B200KV_LAYOUT_NHD 0
+#define B200KV_LAYOUT_HND 1
+
 /* ---- kernel variants (both are CUDA; selectable for A/B measurement) ------------------- */
 #define B200KV_VARIANT_BULK 0 /* cp.async.bulk (TMA engine) through a shared-memory ring    */
 #define B200KV_VARIANT_LDG 1  /* 128-bit ld.global.nc / st.global vector copy               */
@@ -169,6 +179,8 @@ typedef struct b200kv_engine_config {
   int32_t variant;           /* B200KV_VARIANT_*                                             */
   int32_t stages;            /* smem ring depth for BULK (0 = default)                       */
   int32_t ctas_per_sm;       /* persistent CTAs per SM (0 = default)                         */
+  int32_t kv_layout;         /* B200KV_LAYOUT_*: order inside one (block, K|V) tile            */
+  int32_t reserved;
 } b200kv_engine_config;
 
 typedef struct b200kv_engine_stats {

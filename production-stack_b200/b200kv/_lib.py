@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb200kv.so")
 
 FMT_RAW, FMT_FP8 = 0, 1
 VARIANT_BULK, VARIANT_LDG = 0, 1
+LAYOUT_NHD, LAYOUT_HND = 0, 1
 POOL_CREATE, POOL_ATTACH, POOL_CREATE_OR_ATTACH = 1, 2, 3
 
 OK, EINVAL, ENOMEM, ENODEV, ENOENT, EEXIST, ENOSPC, ENOTSUP, EBUSY = 0, -22, -12, -19, -2, -17, -28, -95, -16
@@ -40,7 +41,8 @@ class EngineConfig(C.Structure):
                 ("chunk_tokens", C.c_int32), ("format", C.c_int32),
                 ("block_stride_bytes", C.c_uint64), ("n_blocks", C.c_uint64),
                 ("staging_bytes", C.c_uint64), ("owner", C.c_uint32), ("variant", C.c_int32),
-                ("stages", C.c_int32), ("ctas_per_sm", C.c_int32)]
+                ("stages", C.c_int32), ("ctas_per_sm", C.c_int32), ("kv_layout", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class EngineStats(C.Structure):

@@ -94,7 +94,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._sched: SchedulerState | None = None
         self._controller = None
         if role == KVConnectorRole.SCHEDULER:
-            seed = geom.key_seed(self._model, self._world, 0)
+            seed = self._key_seed(0)
             lease = self.cfg.lookup_lease_ms
             chunk = self._chunk
             pool = self._pool
@@ -109,10 +109,17 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                     role.name, self.kv_role, self._pool_name, self.cfg.max_local_cpu_size_gb, self._chunk,
                     "fp8" if self.cfg.fmt else "raw")
 
+    def _key_seed(self, rank: int) -> int:
+        """Same namespace in both roles: derived from the vLLM config only (the tile layout is a
+        per-process constant of the attention backend, so it need not enter the scheduler's seed;
+        chunks are additionally tagged with their format in the pool)."""
+        return geometry_from_vllm(self._vllm_config, self.cfg).key_seed(self._model, self._world, rank)
+
     # ------------------------------------------------------------------ class-level hooks
     @classmethod
     def get_required_kvcache_layout(cls, vllm_config: "VllmConfig") -> str | None:
-        # kernels address [block][token][head][dim]; HND would need the transposing path
+        # Both tile orders are supported; NHD is preferred when the backend leaves the choice
+        # (on Blackwell vLLM's FlashInfer backend imposes HND, selector.py:124-133).
         return "NHD"
 
     # ------------------------------------------------------------------ worker side
@@ -122,18 +129,19 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         if not tensors:
             raise ValueError("no KV cache tensors to register")
         t0 = tensors[0]
-        k, v, stride, nb, h, d = paged_layout_of(t0, self._block_size)
+        k, v, stride, nb, h, d, tile_layout = paged_layout_of(t0, self._block_size)
         geom0 = geometry_from_vllm(self._vllm_config, self.cfg)
         geom = KVGeometry(n_layers=len(tensors), n_kv_heads=h, head_dim=d, n_blocks=nb,
                           block_tokens=self._block_size, chunk_tokens=self._chunk,
-                          elem_bytes=t0.element_size(), block_stride_bytes=stride, fmt=self.cfg.fmt)
+                          elem_bytes=t0.element_size(), block_stride_bytes=stride, fmt=self.cfg.fmt,
+                          layout=tile_layout)
         if geom.chunk_bytes != geom0.chunk_bytes:
             raise ValueError("KV cache tensors do not match the model geometry the pool was sized for "
                              f"({geom.chunk_bytes} vs {geom0.chunk_bytes} bytes per chunk)")
         rank = getattr(self._vllm_config.parallel_config, "rank", 0)
         self._engine = KVEngine(geom, self._pool, device=t0.device.index or 0,
                                 staging_bytes=self.cfg.staging_mb << 20, owner=owner_tag_of(self.cfg.instance_id),
-                                variant=self.cfg.variant, key_seed=geom0.key_seed(self._model, self._world, rank))
+                                variant=self.cfg.variant, key_seed=self._key_seed(rank))
         self._engine.register_kv_caches(tensors)
         self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role)
         if self.cfg.enable_controller and self.cfg.controller_pull_url and rank == 0:

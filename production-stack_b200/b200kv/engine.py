@@ -71,6 +71,7 @@ class KVGeometry:
     elem_bytes: int = 2
     block_stride_bytes: int = 0   # 0 -> dense (block_tokens * H * D * elem)
     fmt: int = FMT_RAW
+    layout: int = 0               # LAYOUT_NHD / LAYOUT_HND inside a block
 
     @property
     def token_bytes(self) -> int:
@@ -84,7 +85,7 @@ class KVGeometry:
         """Namespace for chunk keys: same role as LMCache's CacheEngineKey(fmt, model, world_size,
         worker_id, ...) — chunks of different models / shards / formats never alias."""
         tag = f"{model}|{world_size}|{rank}|{self.n_layers}|{self.n_kv_heads}|{self.head_dim}|" \
-              f"{self.elem_bytes}|{self.chunk_tokens}|{self.fmt}".encode()
+              f"{self.elem_bytes}|{self.chunk_tokens}|{self.fmt}|{self.layout}".encode()
         return xxh64(tag, DEFAULT_SEED)
 
     def to_c(self, device: int, staging_bytes: int, owner: int, variant: int, stages: int,
@@ -92,7 +93,7 @@ class KVGeometry:
         return _lib.EngineConfig(device, self.n_layers, self.n_kv_heads, self.head_dim,
                                  self.elem_bytes, self.block_tokens, self.chunk_tokens, self.fmt,
                                  self.stride, self.n_blocks, staging_bytes, owner, variant, stages,
-                                 ctas_per_sm)
+                                 ctas_per_sm, self.layout, 0)
 
     @property
     def chunk_bytes(self) -> int:
@@ -219,7 +220,7 @@ def _stream_ptr(stream) -> C.c_void_p:
 
 
 def paged_layout_of(t, block_tokens: int, layout: str | None = None):
-    """(k_ptr, v_ptr, block_stride_bytes, n_blocks, H, D) of one layer's paged KV tensor.
+    """(k_ptr, v_ptr, block_stride_bytes, n_blocks, H, D, tile_layout) of one layer's paged KV tensor.
     FlashAttention (2, NB, bs, H, D) (vllm/v1/attention/backends/flash_attn.py:140-149) or
     FlashInfer (NB, 2, bs, H, D) (flashinfer.py:357-368); within a block the order must be NHD."""
     if t.dim() != 5:
@@ -235,11 +236,14 @@ def paged_layout_of(t, block_tokens: int, layout: str | None = None):
         blk_stride, kv_stride = t.stride(0) * es, t.stride(1) * es
     if two != 2 or bs != block_tokens:
         raise ValueError(f"KV cache shape {tuple(t.shape)} does not match block size {block_tokens}")
-    if tuple(t.stride()[2:]) != (h * d, d, 1):
-        raise NotImplementedError(
-            "KV cache is not NHD inside a block (strides %s); set the connector's required layout "
-            "to NHD" % (tuple(t.stride()),))
-    return t.data_ptr(), t.data_ptr() + kv_stride, blk_stride, nb, h, d
+    inner = tuple(t.stride()[2:])
+    if inner == (h * d, d, 1):
+        tile_layout = _lib.LAYOUT_NHD
+    elif inner == (d, bs * d, 1):
+        tile_layout = _lib.LAYOUT_HND      # what vLLM's FlashInfer backend uses on Blackwell
+    else:
+        raise NotImplementedError("unsupported order inside a KV block (strides %s)" % (tuple(t.stride()),))
+    return t.data_ptr(), t.data_ptr() + kv_stride, blk_stride, nb, h, d, tile_layout
 
 
 class KVEngine:
@@ -273,9 +277,10 @@ class KVEngine:
         tensors = list(kv_caches.values()) if isinstance(kv_caches, dict) else list(kv_caches)
         ks, vs = [], []
         for t in tensors:
-            k, v, stride, nb, h, d = paged_layout_of(t, self.geom.block_tokens, layout)
+            k, v, stride, nb, h, d, tl = paged_layout_of(t, self.geom.block_tokens, layout)
             if stride != self.geom.stride or h != self.geom.n_kv_heads or d != self.geom.head_dim \
-                    or nb < self.geom.n_blocks or t.element_size() != self.geom.elem_bytes:
+                    or nb < self.geom.n_blocks or t.element_size() != self.geom.elem_bytes \
+                    or tl != self.geom.layout:
                 raise ValueError("KV cache tensor does not match the engine geometry")
             ks.append(k)
             vs.append(v)

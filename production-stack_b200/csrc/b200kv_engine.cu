@@ -102,6 +102,8 @@ struct Geometry {
   uint64_t chunk_bytes;
   uint64_t scales_off;    // FP8 only
   uint32_t fmt_token_bytes;
+  bool hnd;               // [H][bs][D] inside a block (B200KV_LAYOUT_HND)
+  uint32_t row_bytes;     // D*elem
 };
 
 int make_geometry(const b200kv_engine_config* c, Geometry* g) {
@@ -117,7 +119,11 @@ int make_geometry(const b200kv_engine_config* c, Geometry* g) {
   g->C = c->chunk_tokens;
   g->planes = 2u * g->L;
   g->token_bytes = g->H * g->D * g->elem;
+  g->row_bytes = g->D * g->elem;
+  if (c->kv_layout != B200KV_LAYOUT_NHD && c->kv_layout != B200KV_LAYOUT_HND) return B200KV_EINVAL;
+  g->hnd = c->kv_layout == B200KV_LAYOUT_HND;
   if (g->token_bytes % 16) return B200KV_EINVAL;  // 16-byte vectors / bulk-copy granularity
+  if (g->hnd && g->row_bytes % 16) return B200KV_EINVAL;
   if (c->format == B200KV_FMT_RAW) {
     g->fmt_token_bytes = g->token_bytes;
     g->slab_bytes = static_cast<uint64_t>(g->C) * g->token_bytes;
@@ -125,6 +131,7 @@ int make_geometry(const b200kv_engine_config* c, Geometry* g) {
     g->chunk_bytes = g->slab_bytes * g->planes;
   } else if (c->format == B200KV_FMT_FP8) {
     if (g->elem != 2) return B200KV_ENOTSUP;  // source must be bf16
+    if (g->hnd) return B200KV_ENOTSUP;        // FP8 kernels address NHD tiles (this round)
     if (g->H > kMaxHeads) return B200KV_ENOTSUP;
     if (g->C % kCluster) return B200KV_EINVAL;
     if ((g->D * 2) % 16) return B200KV_EINVAL;
@@ -203,32 +210,50 @@ int env_int(const char* name, int dflt) {
 // ---- run construction (host) -----------------------------------------------------------------
 // slot_mapping[i] for op-relative token i (vllm_v1_adapter.py:368-375).  A run never crosses a
 // vLLM block or a chunk boundary, so both sides of every run are contiguous byte ranges.
+// For HND tiles a run additionally stops at every chunk-side tile boundary, and runs are split
+// into `full` (one whole aligned block on both sides: a contiguous tile, moved by the bulk kernel
+// exactly like NHD) and `partial` (moved per head by kv_hnd_partial_kernel).  NHD: all `full`.
+struct RunSink {
+  std::vector<Run>* full;
+  std::vector<Run>* partial;
+  bool hnd;
+  int32_t bs;
+  bool both_paged;  // peer pull: `b` is a paged slot too
+  void push(const Run& r) const {
+    if (!hnd) { full->push_back(r); return; }
+    const bool whole = r.n == bs && (r.a % bs) == 0 && (r.b % bs) == 0;
+    (whole ? full : partial)->push_back(r);
+  }
+};
+
 int build_runs(const b200kv_ctx* ctx, const int64_t* slots, int64_t tok_begin, int64_t tok_end,
-               int64_t b_shift, std::vector<Run>* runs) {
+               int64_t b_shift, std::vector<Run>* full, std::vector<Run>* partial) {
   const Geometry& g = ctx->g;
+  const RunSink sink{full, partial, g.hnd, static_cast<int32_t>(g.bs), false};
   const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
   Run cur{0, 0, 0};
   for (int64_t i = tok_begin; i < tok_end; ++i) {
     const int64_t s = slots[i];
     if (s < 0 || s >= max_slot) return B200KV_EINVAL;
     const bool extend = cur.n > 0 && s == static_cast<int64_t>(cur.a) + cur.n && (s % g.bs) != 0 &&
-                        (i % g.C) != 0;
+                        (i % g.C) != 0 && !(g.hnd && ((i - b_shift) % g.bs) == 0);
     if (extend) {
       ++cur.n;
     } else {
-      if (cur.n) runs->push_back(cur);
+      if (cur.n) sink.push(cur);
       cur.a = static_cast<int32_t>(s);
       cur.b = static_cast<int32_t>(i - b_shift);
       cur.n = 1;
     }
   }
-  if (cur.n) runs->push_back(cur);
+  if (cur.n) sink.push(cur);
   return B200KV_OK;
 }
 
 int build_pull_runs(const b200kv_ctx* ctx, const Peer& peer, const int64_t* src, const int64_t* dst,
-                    int64_t n, std::vector<Run>* runs) {
+                    int64_t n, std::vector<Run>* full, std::vector<Run>* partial) {
   const Geometry& g = ctx->g;
+  const RunSink sink{full, partial, g.hnd, static_cast<int32_t>(g.bs), true};
   const int64_t max_dst = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
   const int64_t max_src = static_cast<int64_t>(peer.n_blocks) * g.bs;
   Run cur{0, 0, 0};
@@ -240,13 +265,13 @@ int build_pull_runs(const b200kv_ctx* ctx, const Peer& peer, const int64_t* src,
     if (extend) {
       ++cur.n;
     } else {
-      if (cur.n) runs->push_back(cur);
+      if (cur.n) sink.push(cur);
       cur.a = static_cast<int32_t>(s);
       cur.b = static_cast<int32_t>(d);
       cur.n = 1;
     }
   }
-  if (cur.n) runs->push_back(cur);
+  if (cur.n) sink.push(cur);
   return B200KV_OK;
 }
 
@@ -354,6 +379,12 @@ int launch_copy(b200kv_ctx* ctx, const CopyParams& p, cudaStream_t s) {
   return launch_bulk<MODE>(ctx, p, s);
 }
 
+// format tag recorded with a chunk: a pool shared by engines of different tile order or codec
+// never hands one engine's bytes to another
+uint32_t pool_fmt(const b200kv_ctx* ctx) {
+  return static_cast<uint32_t>(ctx->cfg.format) | (static_cast<uint32_t>(ctx->cfg.kv_layout) << 8);
+}
+
 PagedSide local_side(const b200kv_ctx* ctx) {
   PagedSide s;
   s.bases = ctx->d_bases;
@@ -379,6 +410,42 @@ CopyParams make_copy_params(const b200kv_ctx* ctx, const uint8_t* dev_table, con
   p.piece_tokens = ctx->piece_tokens;
   p.total_units = p.n_runs * p.n_planes * p.pieces;
   return p;
+}
+
+template <int MODE>
+int launch_hnd_partial(b200kv_ctx* ctx, const CopyParams& cp, const Run* runs, uint32_t n_runs, cudaStream_t s) {
+  if (n_runs == 0) return B200KV_OK;
+  HndParams p{};
+  p.paged = cp.paged;
+  p.peer = cp.peer;
+  p.chunk = cp.chunk;
+  p.runs = runs;
+  p.n_runs = n_runs;
+  p.n_planes = ctx->g.planes;
+  p.n_heads = ctx->g.H;
+  p.row_bytes = ctx->g.row_bytes;
+  p.total_units = n_runs * p.n_planes * p.n_heads;
+  const uint32_t grid = std::min<uint32_t>(p.total_units, static_cast<uint32_t>(ctx->sm_count) * 16u);
+  kv_hnd_partial_kernel<MODE><<<grid, 128, 0, s>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++ctx->stats.n_kernel_launches;
+  return B200KV_OK;
+}
+
+// runs [run_begin, +n_full) are whole tiles (or anything, for NHD); the next n_partial are HND
+// partial-tile runs.  `peer` non-null selects the pull source.
+template <int MODE>
+int launch_copy_runs(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv, size_t run_begin,
+                     size_t n_full, size_t n_partial, cudaStream_t s, const Peer* peer = nullptr) {
+  CopyParams p = make_copy_params(ctx, dev_table, tv, run_begin, n_full);
+  if (peer) {
+    p.peer.bases = peer->d_bases;
+    p.peer.block_stride = peer->block_stride;
+  }
+  int rc = B200KV_OK;
+  if (n_full) rc = launch_copy<MODE>(ctx, p, s);
+  if (rc) return rc;
+  return launch_hnd_partial<MODE>(ctx, p, p.runs + n_full, static_cast<uint32_t>(n_partial), s);
 }
 
 int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
@@ -679,9 +746,11 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint32_t n_chunks = static_cast<uint32_t>((n_tokens + g.C - 1) / g.C);
 
-  std::vector<Run> runs;
-  int rc = build_runs(ctx, slots, 0, n_tokens, 0, &runs);
+  std::vector<Run> runs, partial;
+  int rc = build_runs(ctx, slots, 0, n_tokens, 0, &runs, &partial);
   if (rc) return rc;
+  const size_t n_full = runs.size(), n_part = partial.size();
+  runs.insert(runs.end(), partial.begin(), partial.end());
   TableView tv;
   rc = table_acquire(ctx, runs.size(), n_chunks, &tv);
   if (rc) return rc;
@@ -706,8 +775,8 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
     rc = is_gather ? launch_fp8_store(ctx, tv.slot->dev, tv, n_chunks, static_cast<uint32_t>(n_tokens), s)
                    : launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), s);
   } else {
-    const CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, 0, runs.size());
-    rc = is_gather ? launch_copy<kStore>(ctx, p, s) : launch_copy<kLoad>(ctx, p, s);
+    rc = is_gather ? launch_copy_runs<kStore>(ctx, tv.slot->dev, tv, 0, n_full, n_part, s)
+                   : launch_copy_runs<kLoad>(ctx, tv.slot->dev, tv, 0, n_full, n_part, s);
   }
   if (rc) return rc;
   rc = timing_end(ctx, which, s);
@@ -749,8 +818,8 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
   for (int32_t c = 0; c < n_chunks; ++c) {
     const uint32_t n_tok = static_cast<uint32_t>(std::min<int64_t>(g.C, n_tokens - static_cast<int64_t>(c) * g.C));
     uint32_t slot = 0;
-    const int rc = b200kv_pool_reserve(ctx->pool, keys[c], static_cast<int32_t>(n_tok),
-                                       static_cast<uint32_t>(ctx->cfg.format), ctx->cfg.owner, &slot);
+    const int rc = b200kv_pool_reserve(ctx->pool, keys[c], static_cast<int32_t>(n_tok), pool_fmt(ctx),
+                                       ctx->cfg.owner, &slot);
     if (rc == B200KV_OK) todo.push_back({c, slot, n_tok});
     else if (rc != B200KV_EEXIST && rc != B200KV_ENOSPC) return rc;
   }
@@ -772,7 +841,7 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
   const size_t n_stage = ctx->n_store_slots;
   for (size_t b0 = 0; b0 < todo.size(); b0 += n_stage) {
     const size_t nb = std::min(n_stage, todo.size() - b0);
-    std::vector<Run> runs;
+    std::vector<Run> runs, partial;
     std::vector<uint32_t> offs(nb + 1);
     std::vector<uint64_t> addrs(nb);
     std::vector<uint32_t> sidx(nb);
@@ -782,7 +851,7 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       offs[i] = static_cast<uint32_t>(runs.size());
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       // dense op-relative token index: chunk i of this batch starts at i*C
-      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs);
+      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs, &partial);
       if (rc) return rc;
       sidx[i] = ctx->store_next;
       ctx->store_next = (ctx->store_next + 1) % static_cast<uint32_t>(n_stage);
@@ -791,6 +860,8 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       batch_tokens = static_cast<uint32_t>(i) * g.C + t.n_tok;
     }
     offs[nb] = static_cast<uint32_t>(runs.size());
+    const size_t n_full = runs.size(), n_part = partial.size();
+    runs.insert(runs.end(), partial.begin(), partial.end());
     TableView tv;
     int rc = table_acquire(ctx, runs.size(), nb, &tv);
     if (rc) return rc;
@@ -806,8 +877,7 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       // a partial chunk is always the last of the op, hence the last of its batch
       rc = launch_fp8_store(ctx, tv.slot->dev, tv, static_cast<uint32_t>(nb), batch_tokens, ctx->s_gather);
     } else {
-      const CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, 0, runs.size());
-      rc = launch_copy<kStore>(ctx, p, ctx->s_gather);
+      rc = launch_copy_runs<kStore>(ctx, tv.slot->dev, tv, 0, n_full, n_part, ctx->s_gather);
     }
     if (rc) return rc;
     rc = timing_end(ctx, 0, ctx->s_gather);
@@ -859,7 +929,7 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
     uint32_t slot = 0, fmt = 0;
     int32_t have = 0;
     if (b200kv_pool_acquire(ctx->pool, keys[c], &slot, &have, &fmt) != B200KV_OK) break;
-    if (static_cast<uint32_t>(have) != want || fmt != static_cast<uint32_t>(ctx->cfg.format)) {
+    if (static_cast<uint32_t>(have) != want || fmt != pool_fmt(ctx)) {
       b200kv_pool_release(ctx->pool, keys[c]);
       break;
     }
@@ -889,14 +959,19 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
     const size_t nb = std::min(n_stage, todo.size() - b0);
     std::vector<Run> runs;
     std::vector<uint32_t> offs(nb + 1);
+    std::vector<uint32_t> n_full_of(nb);
     std::vector<uint64_t> addrs(nb);
     std::vector<uint32_t> sidx(nb);
     for (size_t i = 0; i < nb; ++i) {
       const Todo& t = todo[b0 + i];
       offs[i] = static_cast<uint32_t>(runs.size());
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
-      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs);
+      std::vector<Run> cf, cp;  // per chunk: whole tiles first, then HND partial-tile runs
+      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf, &cp);
       if (rc) return rc;
+      n_full_of[i] = static_cast<uint32_t>(cf.size());
+      runs.insert(runs.end(), cf.begin(), cf.end());
+      runs.insert(runs.end(), cp.begin(), cp.end());
       sidx[i] = ctx->n_store_slots + ctx->load_next;
       ctx->load_next = (ctx->load_next + 1) % static_cast<uint32_t>(n_stage);
       addrs[i] = reinterpret_cast<uint64_t>(ctx->d_staging) + static_cast<uint64_t>(sidx[i]) * g.chunk_bytes;
@@ -926,8 +1001,7 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
       if (ctx->cfg.format == B200KV_FMT_FP8) {
         rc = launch_fp8_load(ctx, tv.slot->dev, tv, r0, rn, ctx->s_scatter);
       } else {
-        const CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, r0, rn);
-        rc = launch_copy<kLoad>(ctx, p, ctx->s_scatter);
+        rc = launch_copy_runs<kLoad>(ctx, tv.slot->dev, tv, r0, n_full_of[i], rn - n_full_of[i], ctx->s_scatter);
       }
       if (rc) return rc;
       rc = timing_end(ctx, 1, ctx->s_scatter);
@@ -1127,9 +1201,11 @@ extern "C" int b200kv_peer_pull_async(b200kv_ctx* ctx, int32_t peer_id, const in
   cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
   *ticket = 0;
 
-  std::vector<Run> runs;
-  int rc = build_pull_runs(ctx, peer, src_slots, dst_slots, n_tokens, &runs);
+  std::vector<Run> runs, partial;
+  int rc = build_pull_runs(ctx, peer, src_slots, dst_slots, n_tokens, &runs, &partial);
   if (rc) return rc;
+  const size_t n_full = runs.size(), n_part = partial.size();
+  runs.insert(runs.end(), partial.begin(), partial.end());
   TableView tv;
   rc = table_acquire(ctx, runs.size(), 1, &tv);
   if (rc) return rc;
@@ -1146,13 +1222,10 @@ extern "C" int b200kv_peer_pull_async(b200kv_ctx* ctx, int32_t peer_id, const in
   rc = table_upload(ctx, tv, ctx->s_scatter);
   if (rc) return rc;
 
-  CopyParams p = make_copy_params(ctx, tv.slot->dev, tv, 0, runs.size());
-  p.peer.bases = peer.d_bases;
-  p.peer.block_stride = peer.block_stride;
   timing_reset(ctx, 2);
   rc = timing_begin(ctx, 2, ctx->s_scatter);
   if (rc) return rc;
-  rc = launch_copy<kPull>(ctx, p, ctx->s_scatter);
+  rc = launch_copy_runs<kPull>(ctx, tv.slot->dev, tv, 0, n_full, n_part, ctx->s_scatter, &peer);
   if (rc) return rc;
   rc = timing_end(ctx, 2, ctx->s_scatter);
   if (rc) return rc;

@@ -279,6 +279,63 @@ __global__ void __launch_bounds__(256) kv_ldg_copy_kernel(const CopyParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// HND tiles ([H][block_tokens][D] inside a block).  A whole-block run is one contiguous tile and
+// goes through the kernels above unchanged (the chunk stores tiles verbatim).  Runs that cover
+// only part of a tile — the ragged tail of a request, or token-granular mappings — are moved
+// per head by this kernel: one unit = (run, plane, head) = n * D * elem contiguous bytes.
+// ---------------------------------------------------------------------------------------------
+struct HndParams {
+  PagedSide paged, peer;
+  ChunkSide chunk;       // chunk.token_bytes = H*D*elem; a tile = block_tokens * token_bytes
+  const Run* runs;
+  uint32_t n_runs, n_planes, n_heads;
+  uint32_t row_bytes;    // D * elem: one (token, head) row
+  uint32_t total_units;  // n_runs * n_planes * n_heads
+};
+
+__device__ __forceinline__ uint64_t paged_addr_hnd(const PagedSide& s, uint32_t plane, uint32_t slot,
+                                                   uint32_t h, uint32_t row_bytes) {
+  const uint32_t blk = slot / s.block_tokens;
+  const uint32_t off = slot - blk * s.block_tokens;
+  return __ldg(s.bases + plane) + static_cast<uint64_t>(blk) * s.block_stride +
+         static_cast<uint64_t>(h) * s.block_tokens * row_bytes + static_cast<uint64_t>(off) * row_bytes;
+}
+__device__ __forceinline__ uint64_t chunk_addr_hnd(const ChunkSide& s, uint32_t plane, uint32_t tok,
+                                                   uint32_t h, uint32_t block_tokens, uint32_t row_bytes) {
+  const uint32_t c = tok / s.chunk_tokens;
+  const uint32_t t = tok - c * s.chunk_tokens;
+  const uint32_t tile = t / block_tokens;
+  const uint32_t off = t - tile * block_tokens;
+  return __ldg(s.chunk_addrs + c) + static_cast<uint64_t>(plane) * s.slab_bytes +
+         static_cast<uint64_t>(tile) * block_tokens * s.token_bytes +
+         static_cast<uint64_t>(h) * block_tokens * row_bytes + static_cast<uint64_t>(off) * row_bytes;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) kv_hnd_partial_kernel(const HndParams p) {
+  for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x) {
+    const uint32_t h = ui % p.n_heads;
+    const uint32_t t = ui / p.n_heads;
+    const uint32_t plane = t % p.n_planes;
+    const Run run = p.runs[t / p.n_planes];
+    uint64_t src, dst;
+    if (MODE == kStore) {
+      src = paged_addr_hnd(p.paged, plane, static_cast<uint32_t>(run.a), h, p.row_bytes);
+      dst = chunk_addr_hnd(p.chunk, plane, static_cast<uint32_t>(run.b), h, p.paged.block_tokens, p.row_bytes);
+    } else if (MODE == kLoad) {
+      src = chunk_addr_hnd(p.chunk, plane, static_cast<uint32_t>(run.b), h, p.paged.block_tokens, p.row_bytes);
+      dst = paged_addr_hnd(p.paged, plane, static_cast<uint32_t>(run.a), h, p.row_bytes);
+    } else {
+      src = paged_addr_hnd(p.peer, plane, static_cast<uint32_t>(run.a), h, p.row_bytes);
+      dst = paged_addr_hnd(p.paged, plane, static_cast<uint32_t>(run.b), h, p.row_bytes);
+    }
+    const uint32_t nvec = (static_cast<uint32_t>(run.n) * p.row_bytes) >> 4;
+    for (uint32_t i = threadIdx.x; i < nvec; i += 128)
+      st_na_v4(reinterpret_cast<uint4*>(dst) + i, ld_nc_v4(reinterpret_cast<const uint4*>(src) + i));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP8 store.  grid = (kCluster * n_slabs), cluster (kCluster,1,1); slab = (chunk c, plane).
 // CTA `rank` owns tokens [rank*W, rank*W+W) of the chunk, W = C / kCluster.
 // ---------------------------------------------------------------------------------------------

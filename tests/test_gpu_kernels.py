@@ -235,8 +235,10 @@ def test_bad_arguments_are_errors_not_crashes():
     with pytest.raises(b200kv.B200KVError):
         eng.store(np.arange(16), None, np.arange(16))       # no pool attached
     hnd = [t.permute(0, 1, 3, 2, 4).contiguous().permute(0, 1, 3, 2, 4) for t in dev]
+    with pytest.raises(ValueError):
+        eng.register_kv_caches(hnd)                          # HND tensors on an engine built for NHD
     with pytest.raises(NotImplementedError):
-        eng.register_kv_caches(hnd)                          # HND inside a block
+        eng.register_kv_caches([t.permute(0, 1, 4, 3, 2).contiguous().permute(0, 1, 4, 3, 2) for t in dev])
     eng.close()
 
 
@@ -388,3 +390,120 @@ def test_fp8_store_token_granular_and_block_mappings(n_tok):
         s = c * cb + so
         assert np.array_equal(got[s:s + 2 * p["L"] * p["H"] * 4], want[s:s + 2 * p["L"] * p["H"] * 4])
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# HND tiles: [H][block_tokens][D] inside a block — the layout vLLM's FlashInfer backend imposes on
+# Blackwell.  Logical content (what the model sees) must equal the oracle's, whatever the order.
+# ------------------------------------------------------------------------------------------------
+def to_dev_hnd(layers, dev="cuda:0"):
+    """host logical (2, NB, bs, H, D) -> device tensors shaped like vLLM's FlashInfer cache:
+    logical (NB, 2, bs, H, D) over physical (NB, 2, H, bs, D)."""
+    out = []
+    for l in layers:
+        t = torch.from_numpy(l.view(np.int16)).view(torch.bfloat16).to(dev)
+        phys = t.permute(1, 0, 3, 2, 4).contiguous()          # (NB, 2, H, bs, D)
+        out.append(phys.permute(0, 1, 3, 2, 4))               # logical view, HND strides
+    return out
+
+
+def logical_bits(t):  # (NB, 2, bs, H, D) logical view -> numpy (2, NB, bs, H, D)
+    return bits_of(t.permute(1, 0, 2, 3, 4).contiguous())
+
+
+@pytest.mark.parametrize("n_tok", [1, 15, 16, 17, 40, 256, 300, 1000])
+def test_hnd_store_retrieve_matches_oracle(n_tok):
+    need_gpu()
+    p = SMALL
+    rng = np.random.default_rng(500 + n_tok)
+    host = mk_host_layers(rng, p["L"], p["NB"], p["bs"], p["H"], p["D"])
+    dev = to_dev_hnd(host)
+    assert tuple(dev[0].stride()[2:]) == (p["D"], p["bs"] * p["D"], 1)
+    geom = KVGeometry(p["L"], p["H"], p["D"], p["NB"], p["bs"], p["C"], 2, 2 * p["bs"] * p["H"] * p["D"] * 2,
+                      FMT_RAW, b200kv._lib.LAYOUT_HND)
+    pool = KVPool(None, 8 * geom.chunk_bytes, geom.chunk_bytes, 1)
+    eng = KVEngine(geom, pool, 0, staging_bytes=4 * geom.chunk_bytes)
+    eng.register_kv_caches(dev)
+    if n_tok == 40:      # token-granular: every token in another block, unaligned on both sides
+        sm = rng.permutation(p["NB"] * p["bs"])[:n_tok].astype(np.int64)
+        dm = rng.permutation(p["NB"] * p["bs"])[:n_tok].astype(np.int64)
+    else:
+        nb = (n_tok + 15) // 16
+        sm = ko.slot_mapping_from_blocks(rng.permutation(p["NB"])[:nb], 16, n_tok)
+        dm = ko.slot_mapping_from_blocks(rng.permutation(p["NB"])[:nb], 16, n_tok)
+    toks = rng.integers(0, 1000, n_tok).astype(np.int32)
+    eng.wait(eng.store(toks, None, sm))
+    assert eng.lookup(toks) == n_tok
+    for t in dev:
+        t.zero_()
+    ret = eng.retrieve(toks, None, dm)
+    torch.cuda.synchronize()
+    assert ret.all()
+    want = [np.zeros_like(l) for l in host]
+    oe = ko.OracleEngine(p["C"])
+    oe.store(toks, np.ones(n_tok, bool), host, sm)
+    oe.retrieve(toks, np.ones(n_tok, bool), want, dm)
+    for a, b in zip(dev, want):
+        assert np.array_equal(logical_bits(a), b)
+    # device-resident halves too, and the chunk keeps whole tiles verbatim
+    buf = torch.zeros(((n_tok + p["C"] - 1) // p["C"]) * geom.chunk_bytes, dtype=torch.uint8, device="cuda:0")
+    src = to_dev_hnd(host)
+    e2 = KVEngine(geom, None, 0, staging_bytes=0)
+    e2.register_kv_caches(src)
+    e2.gather(sm, buf.data_ptr())
+    if n_tok >= 16 and n_tok != 40:
+        tile = p["bs"] * p["H"] * p["D"] * 2
+        first_tile = buf[:tile].cpu().numpy().view(np.uint16).reshape(p["H"], p["bs"], p["D"])
+        blk = int(sm[0]) // 16
+        assert np.array_equal(first_tile, host[0][0, blk].transpose(1, 0, 2))     # layer 0, K, [H][bs][D]
+    for t in src:
+        t.zero_()
+    e2.scatter(dm, buf.data_ptr())
+    torch.cuda.synchronize()
+    for a, b in zip(src, want):
+        assert np.array_equal(logical_bits(a), b)
+    e2.close()
+    eng.close()
+    pool.close()
+
+
+def test_hnd_peer_pull_and_format_isolation():
+    need_gpu()
+    L, NB, bs, H, D = 2, 64, 16, 8, 128
+    rng = np.random.default_rng(91)
+    host = mk_host_layers(rng, L, NB, bs, H, D)
+    geom = KVGeometry(L, H, D, NB, bs, 256, 2, 2 * bs * H * D * 2, FMT_RAW, b200kv._lib.LAYOUT_HND)
+    producer = to_dev_hnd(host)
+    local = to_dev_hnd([np.zeros_like(l) for l in host])
+    eng = KVEngine(geom, None, 0, staging_bytes=0)
+    eng.register_kv_caches(local)
+    eng.import_peer_ptrs(2, 0, [t[:, 0].data_ptr() for t in producer], [t[:, 1].data_ptr() for t in producer])
+    n = 200
+    src = np.concatenate([ko.slot_mapping_from_blocks(rng.permutation(NB)[:10], 16, 160),
+                          rng.permutation(NB * bs)[:40].astype(np.int64)])          # whole tiles + ragged
+    dst = np.concatenate([ko.slot_mapping_from_blocks(rng.permutation(NB)[:10], 16, 160),
+                          (np.arange(40) + 11 * 16 * 3 + 5).astype(np.int64)])
+    dst_blocks_used = set(int(x) // 16 for x in dst[:160])
+    dst[160:] = [s for s in range(NB * bs) if s // 16 not in dst_blocks_used][5:45]
+    eng.wait(eng.peer_pull(2, src, dst))
+    torch.cuda.synchronize()
+    got = ko.gather_tokens([logical_bits(t) for t in local], dst)
+    assert np.array_equal(got, ko.gather_tokens(host, src))
+    eng.close()
+    # a pool shared by an NHD and an HND engine never serves one's chunks to the other
+    g_n = KVGeometry(L, H, D, NB, bs, 256)
+    g_h = KVGeometry(L, H, D, NB, bs, 256, 2, 2 * bs * H * D * 2, FMT_RAW, b200kv._lib.LAYOUT_HND)
+    pool = KVPool(None, 4 * g_n.chunk_bytes, g_n.chunk_bytes, 1)
+    e_n = KVEngine(g_n, pool, 0, staging_bytes=2 * g_n.chunk_bytes, key_seed=1)
+    e_h = KVEngine(g_h, pool, 0, staging_bytes=2 * g_h.chunk_bytes, key_seed=1)
+    e_n.register_kv_caches(to_dev(host))
+    e_h.register_kv_caches(local)
+    toks = np.arange(256, dtype=np.int32)
+    sm = ko.slot_mapping_from_blocks(np.arange(16), 16, 256)
+    e_n.wait(e_n.store(toks, None, sm))
+    assert e_h.retrieve(toks, None, sm).sum() == 0 and e_n.retrieve(toks, None, sm).all()
+    e_n.close()
+    e_h.close()
+    pool.close()
+    with pytest.raises(b200kv.B200KVError):
+        KVEngine(KVGeometry(L, H, D, NB, bs, 256, 2, 0, FMT_FP8, b200kv._lib.LAYOUT_HND), None, 0, staging_bytes=0)

@@ -37,7 +37,10 @@ def main():
     words += [str(i) for i in range(10)]
     words += [chr(c) for c in range(ord("a"), ord("z") + 1) if chr(c) not in words]
     words += [chr(c) for c in range(ord("A"), ord("Z") + 1) if chr(c) not in words]
-    vocab = {w: i for i, w in enumerate(dict.fromkeys(words))}
+    words = list(dict.fromkeys(words))
+    # fill the whole model vocabulary so every id a random-init model samples decodes to text
+    words += [f"w{i}" for i in range(len(words), cfg["vocab_size"])]
+    vocab = {w: i for i, w in enumerate(words)}
     tok = Tokenizer(models.WordLevel(vocab=vocab, unk_token="<unk>"))
     tok.pre_tokenizer = pre_tokenizers.Sequence([pre_tokenizers.WhitespaceSplit(), pre_tokenizers.Punctuation(),
                                                  pre_tokenizers.Digits(individual_digits=True)])

@@ -37,6 +37,7 @@ def question(k: int) -> str:
 async def one_request(session, base_url, model, messages, max_tokens, uid):
     t0 = time.time()
     first = None
+    first_chunk = None
     text = []
     usage = {}
     body = {"model": model, "messages": messages, "temperature": 0, "stream": True, "max_tokens": max_tokens,
@@ -56,6 +57,8 @@ async def one_request(session, base_url, model, messages, max_tokens, uid):
             ch = obj.get("choices") or []
             if not ch:
                 continue
+            if first_chunk is None:
+                first_chunk = time.time()
             delta = ch[0].get("delta", {})
             piece = delta.get("content") or delta.get("reasoning_content")
             if piece:
@@ -63,7 +66,10 @@ async def one_request(session, base_url, model, messages, max_tokens, uid):
                     first = time.time()
                 text.append(piece)
     t1 = time.time()
-    first = first if first is not None else t0
+    # the harness falls back to start_time (TTFT 0) when no text ever arrives
+    # (multi-round-qa.py:160-166); with random-init weights an id may detokenise to "" — use the
+    # first streamed chunk in that case so the number stays meaningful
+    first = first if first is not None else (first_chunk if first_chunk is not None else t0)
     return {"body": "".join(text), "ttft": first - t0, "generation_time": t1 - first,
             "prompt_tokens": usage.get("prompt_tokens", 0), "generation_tokens": usage.get("completion_tokens", 0),
             "launch_time": t0, "finish_time": t1}
