@@ -356,6 +356,45 @@ def run_ours(args):
         eng.close()
         pool.close()
 
+    # ---- host-link ceiling for the e2e number (measured live, rank 0 only, N=1 only) -------------
+    link = None
+    if rank == 0 and world == 1:
+        try:
+            nbytes = 1 << 30
+            h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def timed(fn, reps=3):
+                fn()
+                torch.cuda.synchronize()
+                ev0.record(stream)
+                for _ in range(reps):
+                    fn()
+                ev1.record(stream)
+                torch.cuda.synchronize()
+                return ev0.elapsed_time(ev1) / reps
+
+            def both():
+                s1.wait_stream(stream)
+                s2.wait_stream(stream)
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_a, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    h_b.copy_(d_b, non_blocking=True)
+                stream.wait_stream(s1)
+                stream.wait_stream(s2)
+
+            link = {"h2d_GBps": nbytes / timed(lambda: d_a.copy_(h_a, non_blocking=True)) / 1e6,
+                    "d2h_GBps": nbytes / timed(lambda: h_b.copy_(d_b, non_blocking=True)) / 1e6,
+                    "duplex_total_GBps": 2 * nbytes / timed(both) / 1e6,
+                    "how": "cudaMemcpyAsync of 1 GiB pinned (cudaHostAlloc) buffers, CUDA events, this run"}
+            del h_a, h_b, d_a, d_b
+        except Exception as e:
+            link = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -388,6 +427,10 @@ def run_ours(args):
                      "launch_ms": g_ms, "scatter_launch_ms": s_ms,
                      "scatter_achieved": launch_tokens * ALGO_BYTES_PER_TOKEN / (s_ms * 1e-3) / 1e9,
                      "algo_bytes_per_launch": launch_tokens * ALGO_BYTES_PER_TOKEN, "traffic": traffic},
+        "roofline_e2e": None if not link or "error" in link else {
+            "bound": "pcie", "achieved": e2e_gbps, "peak": link["duplex_total_GBps"], "unit": "GB/s",
+            "frac": e2e_gbps / link["duplex_total_GBps"],
+            "note": "store D2H and retrieve H2D overlap (full duplex); peak = measured duplex pinned copy", **link},
         "cpu_baseline": {"value": cpu_gbps, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                          "sample": cpu_sample, "ms_per_step": cpu_ms},
         "clocks": clocks,

@@ -25,6 +25,7 @@ from . import _lib
 from .adapter import ReqMeta, SchedulerState, WorkerState
 from .config import B200KVConfig
 from .engine import KVEngine, KVGeometry, KVPool, paged_layout_of, xxh64
+from .pd import PDMeta, PDScheduler, PDWorker, first_group, publish_ipc, unpublish_ipc
 
 if TYPE_CHECKING:
     from vllm.config import VllmConfig
@@ -40,6 +41,7 @@ logger = logging.getLogger("b200kv")
 @dataclass
 class B200KVConnectorMetadata(KVConnectorMetadata):
     requests: list[ReqMeta] = field(default_factory=list)
+    pd: PDMeta = field(default_factory=PDMeta)   # disaggregated-prefill pulls / held requests
 
 
 def geometry_from_vllm(vllm_config, cfg: B200KVConfig, n_blocks: int = 1) -> KVGeometry:
@@ -93,7 +95,13 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._worker: WorkerState | None = None
         self._sched: SchedulerState | None = None
         self._controller = None
+        self._engine_id = str(ktc.engine_id or "engine")
+        self._pd: PDScheduler | None = None
+        self._pdw: PDWorker | None = None
+        self._remote_computed: dict[str, int] = {}
         if role == KVConnectorRole.SCHEDULER:
+            self._pd = PDScheduler(self._engine_id, self._block_size,
+                                   lease_s=float(self.cfg.extra.get("pd_lease_s", 120.0)))
             seed = self._key_seed(0)
             lease = self.cfg.lookup_lease_ms
             chunk = self._chunk
@@ -144,6 +152,11 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                                 variant=self.cfg.variant, key_seed=self._key_seed(rank))
         self._engine.register_kv_caches(tensors)
         self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role)
+        try:
+            publish_ipc(self._engine_id, self._engine, t0.device.index or 0)   # peers may pull from us
+            self._pdw = PDWorker(self._engine, self._engine_id, self._block_size)
+        except Exception as e:  # e.g. VMM-allocated cache (sleep mode): P/D pull unavailable, offload still works
+            logger.warning("b200kv: cannot publish CUDA-IPC descriptors (%s); peer pull disabled", e)
         if self.cfg.enable_controller and self.cfg.controller_pull_url and rank == 0:
             from .controller_client import ControllerClient
             self._controller = ControllerClient(
@@ -160,7 +173,11 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
     def start_load_kv(self, forward_context: "ForwardContext", **kwargs: Any) -> None:
         if self._worker is None:
             return
-        self._worker.start_load(self._metas(), stream=torch.cuda.current_stream())
+        stream = torch.cuda.current_stream()
+        md = self._get_connector_metadata()
+        if self._pdw is not None and isinstance(md, B200KVConnectorMetadata) and (md.pd.pulls or md.pd.held):
+            self._pdw.start_pulls(md.pd, stream=stream)
+        self._worker.start_load(self._metas(), stream=stream)
 
     def wait_for_layer_load(self, layer_name: str) -> None:
         return  # loads are ordered before the forward pass on the compute stream (stream wait)
@@ -176,15 +193,58 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
     def get_finished(self, finished_req_ids: set[str]) -> tuple[set[str] | None, set[str] | None]:
         if self._worker is not None:
             self._worker.reap()
+        if self._pdw is not None:
+            sent, _recv = self._pdw.poll()   # loads are synchronous for the scheduler: only sends are reported
+            if sent:
+                return sent, None
         return None, None
 
     def get_block_ids_with_load_errors(self) -> set[int]:
-        return self._worker.take_load_errors() if self._worker is not None else set()
+        bad = self._worker.take_load_errors() if self._worker is not None else set()
+        if self._pdw is not None:
+            bad |= self._pdw.take_failed_blocks()
+        return bad
+
+    # ------------------------------------------------------------------ stats (lmcache:* series)
+    def get_kv_connector_stats(self):
+        """Worker side: deltas since the previous call (base.py:403)."""
+        if self._worker is None or self._pool is None:
+            return None
+        from .metrics import B200KVStats
+        ws = self._worker.stats
+        ps = self._pool.stats()
+        cur = {"num_stored_tokens": ws.num_stored_tokens, "num_loaded_tokens": ws.num_loaded_tokens,
+               "retrieve_seconds": ws.retrieve_seconds, "retrieve_calls": ws.retrieve_calls,
+               "load_shortfalls": ws.num_load_shortfalls,
+               "num_hit_tokens": ps["n_hit_tokens"], "num_requested_tokens": ps["n_requested_tokens"],
+               "retrieve_bytes": ws.num_loaded_tokens * self._engine.geom.payload_bytes_per_token,
+               "store_bytes": ws.num_stored_tokens * self._engine.geom.payload_bytes_per_token}
+        prev = getattr(self, "_stats_prev", {})
+        delta = {k: v - prev.get(k, 0) for k, v in cur.items()}
+        self._stats_prev = cur
+        if not any(delta.values()):
+            return None
+        delta["local_cache_usage_bytes"] = ps["n_used"] * ps["slot_bytes"]
+        delta["local_cache_capacity_bytes"] = ps["n_slots"] * ps["slot_bytes"]
+        return B200KVStats(delta)
+
+    @classmethod
+    def build_kv_connector_stats(cls, data: dict[str, Any] | None = None):
+        from .metrics import B200KVStats
+        return B200KVStats(data=data) if data is not None else B200KVStats()
+
+    @classmethod
+    def build_prom_metrics(cls, vllm_config, metric_types, labelnames, per_engine_labelvalues):
+        from .metrics import B200KVPromMetrics
+        return B200KVPromMetrics(vllm_config, metric_types, labelnames, per_engine_labelvalues)
 
     def shutdown(self):
         if self._controller is not None:
             self._controller.close()
             self._controller = None
+        if self._pdw is not None:
+            unpublish_ipc(self._engine_id)
+            self._pdw = None
         if self._engine is not None:
             self._engine.wait_all()
             self._engine.close()
@@ -195,23 +255,45 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
 
     # ------------------------------------------------------------------ scheduler side
     def get_num_new_matched_tokens(self, request: "Request", num_computed_tokens: int) -> tuple[int | None, bool]:
-        assert self._sched is not None
+        assert self._sched is not None and self._pd is not None
+        remote = self._pd.remote_prefill_tokens(request, num_computed_tokens)
+        if remote is not None:   # decode side of a disaggregated request: pull from the prefiller
+            self._remote_computed[request.request_id] = num_computed_tokens
+            return remote, False
         n = self._sched.num_new_matched_tokens(request.request_id, request.prompt_token_ids or [],
                                                request.num_tokens, num_computed_tokens)
         return n, False
 
     def update_state_after_alloc(self, request: "Request", blocks: "KVCacheBlocks", num_external_tokens: int):
-        assert self._sched is not None
+        assert self._sched is not None and self._pd is not None
+        if request.request_id in self._remote_computed:
+            local = first_group(blocks.get_block_ids()) if blocks is not None else []
+            self._pd.after_alloc(request, local, num_external_tokens, self._remote_computed.pop(request.request_id))
+            self._sched.unfinished[request.request_id] = request
+            return
         self._sched.after_alloc(request, num_external_tokens)
 
     def build_connector_meta(self, scheduler_output: "SchedulerOutput") -> KVConnectorMetadata:
-        assert self._sched is not None
-        return B200KVConnectorMetadata(self._sched.build_meta(scheduler_output))
+        assert self._sched is not None and self._pd is not None
+        return B200KVConnectorMetadata(self._sched.build_meta(scheduler_output), self._pd.build_meta())
 
     def request_finished(self, request: "Request", block_ids: list[int]) -> tuple[bool, dict[str, Any] | None]:
-        # the gather that reads a request's pages is ordered before any later forward pass on the
-        # compute stream, so blocks may be freed immediately (no delay_free)
+        # Offload: the gather that reads a request's pages is ordered before any later forward pass
+        # on the compute stream, so blocks may be freed immediately.  Disaggregated prefill: keep
+        # the pages (delay_free) until the decoder has pulled them (b200kv/pd.py).
+        if self._pd is not None:
+            ok = True
+            st = getattr(request, "status", None)
+            if st is not None:
+                ok = getattr(st, "name", str(st)) in ("FINISHED_LENGTH_CAPPED", "FINISHED_STOPPED")
+            delay, params = self._pd.request_finished(request, block_ids, ok)
+            if delay:
+                return True, params
         return False, None
+
+    def update_connector_output(self, connector_output):
+        if self._pd is not None:
+            self._pd.sending_finished(getattr(connector_output, "finished_sending", None))
 
     def request_finished_all_groups(self, request: "Request", block_ids: tuple[list[int], ...]):
         return self.request_finished(request, block_ids[0] if block_ids else [])

@@ -513,7 +513,9 @@ int copy_chunk(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, cuda
     CU_TRY(cudaMemcpyAsync(dst, src, g.chunk_bytes, kind, s));
     moved = g.chunk_bytes;
   } else {
-    const size_t width = static_cast<size_t>(n_tok) * g.fmt_token_bytes;
+    // HND keeps whole tiles: a ragged tail still occupies its last tile across all heads
+    const uint32_t tok_span = g.hnd ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
+    const size_t width = static_cast<size_t>(tok_span) * g.fmt_token_bytes;
     CU_TRY(cudaMemcpy2DAsync(dst, g.slab_bytes, src, g.slab_bytes, width, g.planes, kind, s));
     moved = width * g.planes;
     if (ctx->cfg.format == B200KV_FMT_FP8) {

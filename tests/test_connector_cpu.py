@@ -106,3 +106,34 @@ def test_lmcache_named_alias_resolves():
             assert callable(getattr(LMCacheConnectorV1Impl, name))   # what lmcache_connector.py:120-354 forwards
     finally:
         sys.path.pop(0)
+
+
+def test_lmcache_prometheus_series_names_and_aggregation():
+    """The series production-stack's Grafana dashboard queries
+    (/root/reference/helm/dashboards/lmcache-dashboard.json:204,295,389,453,517)."""
+    from prometheus_client import CollectorRegistry, Counter, Gauge, Histogram, generate_latest
+
+    from b200kv.connector import B200KVConnector
+    from b200kv.metrics import B200KVStats
+    reg = CollectorRegistry()
+
+    def bind(cls):
+        return lambda **kw: cls(registry=reg, **{k: v for k, v in kw.items() if k != "multiprocess_mode"})
+
+    cfg = fake_vllm_config("prom")
+    pm = B200KVConnector.build_prom_metrics(cfg, {Gauge: bind(Gauge), Counter: bind(Counter), Histogram: bind(Histogram)},
+                                            ["model_name", "engine"], {0: ["synth", "0"]})
+    a = B200KVConnector.build_kv_connector_stats({"num_hit_tokens": 512, "num_requested_tokens": 600,
+                                                  "num_loaded_tokens": 512, "retrieve_seconds": 0.004,
+                                                  "retrieve_calls": 2, "retrieve_bytes": 512 * 131072,
+                                                  "local_cache_usage_bytes": 1 << 30})
+    b = B200KVStats({"num_hit_tokens": 8, "num_requested_tokens": 8, "num_stored_tokens": 256})
+    assert not a.is_empty() and B200KVStats().is_empty()
+    agg = a.aggregate(b)
+    assert agg.data["num_hit_tokens"] == 520 and agg.reduce()["retrieve_GBps"] > 1
+    pm.observe(agg.data, 0)
+    text = generate_latest(reg).decode()
+    for series in ("lmcache:num_hit_tokens_total", "lmcache:num_requested_tokens_total", "lmcache:local_cache_usage",
+                   "lmcache:retrieve_speed_sum", "lmcache:retrieve_speed_count"):
+        assert series in text, series
+    assert 'lmcache:num_hit_tokens_total{engine="0",model_name="synth"} 520.0' in text
