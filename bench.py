@@ -183,6 +183,18 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: the b200kv engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    # keep this rank's host pool on the GPU's own NUMA node (first-touch happens when the pool is
+    # pinned): on a two-socket HGX box half of the GPUs would otherwise cross UPI on every DMA
+    numa = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        numa = sorted(os.sched_getaffinity(0))
+        numa = f"{numa[0]}-{numa[-1]} ({len(numa)} cpus)"
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        numa = f"unavailable: {e!r}"[:80]
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -410,6 +422,10 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    try:  # the CPU baseline may use every host core again
+        os.sched_setaffinity(0, range(os.cpu_count()))
+    except Exception:
+        pass
     cpu_gbps, cpu_ms, cpu_threads, cpu_sample = cpu_oracle_run(3, 1)
     line = {
         "metric": "kv_offload_GBps", "value": value_gbps, "unit": "GB/s", "n_gpus": world,
@@ -434,6 +450,7 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_gbps, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                          "sample": cpu_sample, "ms_per_step": cpu_ms},
         "clocks": clocks,
+        "cpu_affinity_rank0": numa,
         "fp8": fp8,
         "peer_pull": peer,
     }

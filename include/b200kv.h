@@ -64,7 +64,7 @@ extern "C" {
  *      Blackwell (vllm/v1/attention/selector.py:124-133 overrides the connector's wish), i.e. the
  *      layout actually met on a B200.  Whole-block runs move as one contiguous tile in both; a
  *      chunk stores tiles verbatim, so chunks of the two layouts never mix (the layout is part
- *      of the key namespace).  FP8 requires NHD in this round.                               */
+ *      of the pool's per-chunk format tag).                                                  */
 #define B200KV_LAYOUT_NHD 0
 #define B200KV_LAYOUT_HND 1
 

@@ -131,7 +131,7 @@ int make_geometry(const b200kv_engine_config* c, Geometry* g) {
     g->chunk_bytes = g->slab_bytes * g->planes;
   } else if (c->format == B200KV_FMT_FP8) {
     if (g->elem != 2) return B200KV_ENOTSUP;  // source must be bf16
-    if (g->hnd) return B200KV_ENOTSUP;        // FP8 kernels address NHD tiles (this round)
+    if (g->hnd && (g->C / kCluster) % g->bs) return B200KV_ENOTSUP;  // a cluster window = whole tiles
     if (g->H > kMaxHeads) return B200KV_ENOTSUP;
     if (g->C % kCluster) return B200KV_EINVAL;
     if ((g->D * 2) % 16) return B200KV_EINVAL;
@@ -220,7 +220,7 @@ struct RunSink {
   int32_t bs;
   bool both_paged;  // peer pull: `b` is a paged slot too
   void push(const Run& r) const {
-    if (!hnd) { full->push_back(r); return; }
+    if (!hnd || !partial) { full->push_back(r); return; }  // FP8 kernels take one sorted list
     const bool whole = r.n == bs && (r.a % bs) == 0 && (r.b % bs) == 0;
     (whole ? full : partial)->push_back(r);
   }
@@ -463,6 +463,7 @@ int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView&
   p.head_bytes = ctx->g.D * 2;
   p.slab_q_bytes = ctx->g.slab_bytes;
   p.scales_off = ctx->g.scales_off;
+  p.hnd = ctx->g.hnd ? 1u : 0u;
   const size_t smem = static_cast<size_t>(ctx->g.C / kCluster) * ctx->g.token_bytes;
   if (smem > 200 * 1024) return B200KV_ENOTSUP;
   static bool attr_set[8] = {false};
@@ -493,6 +494,7 @@ int launch_fp8_load(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& 
   p.head_bytes = ctx->g.D * 2;
   p.slab_q_bytes = ctx->g.slab_bytes;
   p.scales_off = ctx->g.scales_off;
+  p.hnd = ctx->g.hnd ? 1u : 0u;
   p.total_units = p.n_runs * p.n_planes;
   const size_t smem = static_cast<size_t>(ctx->g.bs) * ctx->g.fmt_token_bytes;
   if (smem > 48 * 1024) return B200KV_ENOTSUP;
@@ -749,7 +751,8 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   const uint32_t n_chunks = static_cast<uint32_t>((n_tokens + g.C - 1) / g.C);
 
   std::vector<Run> runs, partial;
-  int rc = build_runs(ctx, slots, 0, n_tokens, 0, &runs, &partial);
+  const bool fp8 = ctx->cfg.format == B200KV_FMT_FP8;
+  int rc = build_runs(ctx, slots, 0, n_tokens, 0, &runs, fp8 ? nullptr : &partial);
   if (rc) return rc;
   const size_t n_full = runs.size(), n_part = partial.size();
   runs.insert(runs.end(), partial.begin(), partial.end());
@@ -853,7 +856,8 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       offs[i] = static_cast<uint32_t>(runs.size());
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       // dense op-relative token index: chunk i of this batch starts at i*C
-      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs, &partial);
+      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs,
+                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &partial);
       if (rc) return rc;
       sidx[i] = ctx->store_next;
       ctx->store_next = (ctx->store_next + 1) % static_cast<uint32_t>(n_stage);
@@ -969,7 +973,8 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
       offs[i] = static_cast<uint32_t>(runs.size());
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       std::vector<Run> cf, cp;  // per chunk: whole tiles first, then HND partial-tile runs
-      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf, &cp);
+      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf,
+                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &cp);
       if (rc) return rc;
       n_full_of[i] = static_cast<uint32_t>(cf.size());
       runs.insert(runs.end(), cf.begin(), cf.end());

@@ -354,6 +354,7 @@ struct Fp8StoreParams {
   uint32_t n_heads, head_bytes;   // H, D*2
   uint64_t slab_q_bytes;          // C * H * D   (e4m3 bytes per slab)
   uint64_t scales_off;            // byte offset of the (planes, H) fp32 scales inside a chunk
+  uint32_t hnd;                   // tiles are [H][block_tokens][D]; the packed chunk mirrors them
 };
 
 __device__ __forceinline__ uint32_t absmax_u16x2(uint32_t acc, uint32_t w) {
@@ -407,17 +408,30 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
     // L2 round trip instead of a serial chain, and every lane issues its own bulk copy.
     uint32_t mine = 0;
     const uint32_t r0 = p.chunk_run_off[c], r1 = p.chunk_run_off[c + 1];
+    const uint32_t bs = p.paged.block_tokens;
     for (uint32_t r = r0 + threadIdx.x; r < r1; r += 32) {
       const Run run = p.runs[r];
       const int32_t lo = max(run.b, static_cast<int32_t>(win_lo));
       const int32_t hi = min(run.b + run.n, static_cast<int32_t>(win_lo + n_valid));
       if (hi <= lo) continue;
-      const uint32_t bytes = static_cast<uint32_t>(hi - lo) * tb;
-      bulk_g2s(smem + static_cast<size_t>(lo - static_cast<int32_t>(win_lo)) * tb,
-               reinterpret_cast<const void*>(
-                   paged_addr(p.paged, plane, static_cast<uint32_t>(run.a + (lo - run.b)))),
-               bytes, &bar);
-      mine += bytes;
+      const uint32_t slot = static_cast<uint32_t>(run.a + (lo - run.b));
+      const uint32_t rel = static_cast<uint32_t>(lo - static_cast<int32_t>(win_lo));
+      const uint32_t n = static_cast<uint32_t>(hi - lo);
+      if (!p.hnd || (n == bs && (slot % bs) == 0 && (rel % bs) == 0)) {
+        // NHD run, or a whole HND tile: one contiguous piece
+        bulk_g2s(smem + static_cast<size_t>(rel) * tb, reinterpret_cast<const void*>(paged_addr(p.paged, plane, slot)),
+                 n * tb, &bar);
+        mine += n * tb;
+      } else {
+        // partial HND tile: one piece per head (runs never cross a tile on either side)
+        const uint32_t row = p.head_bytes;  // D*2
+        uint8_t* tile = smem + static_cast<size_t>(rel / bs) * bs * tb + static_cast<size_t>(rel % bs) * row;
+        for (uint32_t h = 0; h < p.n_heads; ++h) {
+          bulk_g2s(tile + static_cast<size_t>(h) * bs * row,
+                   reinterpret_cast<const void*>(paged_addr_hnd(p.paged, plane, slot, h, row)), n * row, &bar);
+          mine += n * row;
+        }
+      }
     }
     const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
     // complete_tx may land before this expect_tx: the phase cannot complete until the arrive
@@ -425,22 +439,42 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
   }
   mbar_wait(&bar, 0);
 
-  // ---- per-head absmax over this CTA's tokens: a thread's 16-byte column has a fixed head ----
-  // When a token has fewer than 256 vectors the spare threads split the tokens between them.
   const uint32_t vpt = tb >> 4;  // 16-byte vectors per token
-  const uint32_t groups = vpt < kFp8Threads ? kFp8Threads / vpt : 1;
-  const uint32_t grp = threadIdx.x / vpt;
-  if (grp < groups) {
-    const uint32_t col_step = groups == 1 ? kFp8Threads : vpt;
-    for (uint32_t col = threadIdx.x - grp * vpt; col < vpt; col += col_step) {
-      uint32_t acc = 0;
-      const uint8_t* q = smem + static_cast<size_t>(col) * 16;
-      for (uint32_t t = grp; t < n_valid; t += groups) {
-        const uint4 v = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(t) * tb);
-        acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(acc, v.x), v.y), v.z), v.w);
+  // HND window = W/bs whole tiles [H][bs][D]: vector idx = ((tile*H + h)*bs + row)*rv + c.  With 256
+  // threads and bs*rv == 256 all lanes of a warp share (tile, h) in one iteration.
+  const uint32_t rv = p.head_bytes >> 4;                 // 16-byte vectors per (token, head) row
+  const uint32_t tile_rows = p.paged.block_tokens * rv;  // vectors per (tile, head)
+  const uint32_t hnd_total = (W / p.paged.block_tokens) * p.n_heads * tile_rows;
+  if (p.hnd) {
+    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kFp8Threads) {
+      const uint32_t rowi = (idx / rv) % p.paged.block_tokens;
+      const uint32_t h = (idx / tile_rows) % p.n_heads;
+      const uint32_t tile = idx / (tile_rows * p.n_heads);
+      uint32_t m = 0;
+      if (tile * p.paged.block_tokens + rowi < n_valid) {
+        const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(idx) * 16);
+        const uint32_t acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(0u, v.x), v.y), v.z), v.w);
+        m = max(acc & 0xffffu, acc >> 16);
       }
-      const uint32_t m = max(acc & 0xffffu, acc >> 16);
-      atomicMax(&s_absmax[(col * 16) / p.head_bytes], m);
+      if (m) atomicMax(&s_absmax[h], m);
+    }
+  } else {
+  // ---- per-head absmax over this CTA's tokens: a thread's 16-byte column has a fixed head ----
+    // When a token has fewer than 256 vectors the spare threads split the tokens between them.
+    const uint32_t groups = vpt < kFp8Threads ? kFp8Threads / vpt : 1;
+    const uint32_t grp = threadIdx.x / vpt;
+    if (grp < groups) {
+      const uint32_t col_step = groups == 1 ? kFp8Threads : vpt;
+      for (uint32_t col = threadIdx.x - grp * vpt; col < vpt; col += col_step) {
+        uint32_t acc = 0;
+        const uint8_t* q = smem + static_cast<size_t>(col) * 16;
+        for (uint32_t t = grp; t < n_valid; t += groups) {
+          const uint4 v = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(t) * tb);
+          acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(acc, v.x), v.y), v.z), v.w);
+        }
+        const uint32_t m = max(acc & 0xffffu, acc >> 16);
+        atomicMax(&s_absmax[(col * 16) / p.head_bytes], m);
+      }
     }
   }
   __syncthreads();
@@ -460,6 +494,21 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
   }
   __syncthreads();
 
+  if (p.hnd) {
+    // the packed slab mirrors the tiles at half size: same vector index, 8 bytes each
+    uint8_t* outh = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
+                                               static_cast<uint64_t>(rank * W) * (tb >> 1));
+    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kFp8Threads) {
+      const uint32_t rowi = (idx / rv) % p.paged.block_tokens;
+      const uint32_t h = (idx / tile_rows) % p.n_heads;
+      const uint32_t tile = idx / (tile_rows * p.n_heads);
+      if (tile * p.paged.block_tokens + rowi >= n_valid) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(idx) * 16);
+      st_na_v2(outh + static_cast<size_t>(idx) * 8, quant8(v, s_inv[h]));
+    }
+    cluster_sync_all();
+    return;
+  }
   // ---- quantise from smem, 8-byte coalesced stores ----
   uint8_t* out = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
                                             static_cast<uint64_t>(rank * W) * (tb >> 1));
@@ -494,6 +543,7 @@ struct Fp8LoadParams {
   uint64_t slab_q_bytes;
   uint64_t scales_off;
   uint32_t total_units;
+  uint32_t hnd;
 };
 
 __device__ __forceinline__ uint4 dequant8(const uint2& q, float scale) {
@@ -533,10 +583,13 @@ __global__ void __launch_bounds__(kFp8Threads) kv_fp8_load_kernel(const Fp8LoadP
     const uint32_t c = static_cast<uint32_t>(run.b) / p.chunk_tokens;
     const uint32_t t = static_cast<uint32_t>(run.b) - c * p.chunk_tokens;
     const uint64_t cbase = __ldg(p.chunk_addrs + c);
-    const uint32_t qbytes = static_cast<uint32_t>(run.n) * qtb;
+    const uint32_t bs = p.paged.block_tokens;
+    // NHD: the run's n tokens are contiguous in the packed slab.  HND: fetch the whole packed tile
+    // ([H][bs][D] bytes) the run lives in and pick its rows.
+    const uint32_t q_off = p.hnd ? (t / bs) * bs * qtb : t * qtb;
+    const uint32_t qbytes = p.hnd ? bs * qtb : static_cast<uint32_t>(run.n) * qtb;
     if (threadIdx.x == 0) {
-      bulk_g2s(smem, reinterpret_cast<const void*>(cbase + static_cast<uint64_t>(plane) * p.slab_q_bytes +
-                                                   static_cast<uint64_t>(t) * qtb),
+      bulk_g2s(smem, reinterpret_cast<const void*>(cbase + static_cast<uint64_t>(plane) * p.slab_q_bytes + q_off),
                qbytes, &bar);
       mbar_arrive_expect_tx(&bar, qbytes);
     }
@@ -545,8 +598,25 @@ __global__ void __launch_bounds__(kFp8Threads) kv_fp8_load_kernel(const Fp8LoadP
           reinterpret_cast<const float*>(cbase + p.scales_off)[plane * p.n_heads + threadIdx.x];
     __syncthreads();
     mbar_wait(&bar, phase);
-    uint8_t* dst = reinterpret_cast<uint8_t*>(paged_addr(p.paged, plane, static_cast<uint32_t>(run.a)));
     const uint32_t vpt = tb >> 4;
+    if (p.hnd) {
+      const uint32_t rv = p.head_bytes >> 4;          // 16-byte output vectors per (token, head) row
+      const uint32_t o_src = t % bs;                    // first row inside the packed tile
+      const uint32_t n = static_cast<uint32_t>(run.n);
+      const uint32_t total = p.n_heads * n * rv;
+      for (uint32_t e = threadIdx.x; e < total; e += kFp8Threads) {
+        const uint32_t cc = e % rv;
+        const uint32_t r = (e / rv) % n;
+        const uint32_t h = e / (rv * n);
+        const uint2 q = *reinterpret_cast<const uint2*>(smem + (static_cast<size_t>(h) * bs + o_src + r) * (p.head_bytes >> 1) +
+                                                        static_cast<size_t>(cc) * 8);
+        uint8_t* d = reinterpret_cast<uint8_t*>(paged_addr_hnd(p.paged, plane, static_cast<uint32_t>(run.a), h, p.head_bytes));
+        st_na_v4(d + static_cast<size_t>(r) * p.head_bytes + static_cast<size_t>(cc) * 16, dequant8(q, s_scale[h]));
+      }
+      __syncthreads();
+      continue;
+    }
+    uint8_t* dst = reinterpret_cast<uint8_t*>(paged_addr(p.paged, plane, static_cast<uint32_t>(run.a)));
     const uint32_t nvec = static_cast<uint32_t>(run.n) * vpt;
     if ((kFp8Threads % vpt) == 0) {
       const float sc = s_scale[((threadIdx.x % vpt) * 16) / p.head_bytes];

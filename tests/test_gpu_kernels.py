@@ -411,8 +411,9 @@ def logical_bits(t):  # (NB, 2, bs, H, D) logical view -> numpy (2, NB, bs, H, D
     return bits_of(t.permute(1, 0, 2, 3, 4).contiguous())
 
 
+@pytest.mark.parametrize("fmt", [FMT_RAW, FMT_FP8])
 @pytest.mark.parametrize("n_tok", [1, 15, 16, 17, 40, 256, 300, 1000])
-def test_hnd_store_retrieve_matches_oracle(n_tok):
+def test_hnd_store_retrieve_matches_oracle(n_tok, fmt):
     need_gpu()
     p = SMALL
     rng = np.random.default_rng(500 + n_tok)
@@ -420,7 +421,7 @@ def test_hnd_store_retrieve_matches_oracle(n_tok):
     dev = to_dev_hnd(host)
     assert tuple(dev[0].stride()[2:]) == (p["D"], p["bs"] * p["D"], 1)
     geom = KVGeometry(p["L"], p["H"], p["D"], p["NB"], p["bs"], p["C"], 2, 2 * p["bs"] * p["H"] * p["D"] * 2,
-                      FMT_RAW, b200kv._lib.LAYOUT_HND)
+                      fmt, b200kv._lib.LAYOUT_HND)
     pool = KVPool(None, 8 * geom.chunk_bytes, geom.chunk_bytes, 1)
     eng = KVEngine(geom, pool, 0, staging_bytes=4 * geom.chunk_bytes)
     eng.register_kv_caches(dev)
@@ -440,18 +441,18 @@ def test_hnd_store_retrieve_matches_oracle(n_tok):
     torch.cuda.synchronize()
     assert ret.all()
     want = [np.zeros_like(l) for l in host]
-    oe = ko.OracleEngine(p["C"])
+    oe = ko.OracleEngine(p["C"], "fp8" if fmt == FMT_FP8 else "raw")
     oe.store(toks, np.ones(n_tok, bool), host, sm)
     oe.retrieve(toks, np.ones(n_tok, bool), want, dm)
     for a, b in zip(dev, want):
-        assert np.array_equal(logical_bits(a), b)
+        assert np.array_equal(logical_bits(a), b)       # FP8: same codes and scales => same bf16 bits
     # device-resident halves too, and the chunk keeps whole tiles verbatim
     buf = torch.zeros(((n_tok + p["C"] - 1) // p["C"]) * geom.chunk_bytes, dtype=torch.uint8, device="cuda:0")
     src = to_dev_hnd(host)
     e2 = KVEngine(geom, None, 0, staging_bytes=0)
     e2.register_kv_caches(src)
     e2.gather(sm, buf.data_ptr())
-    if n_tok >= 16 and n_tok != 40:
+    if n_tok >= 16 and n_tok != 40 and fmt == FMT_RAW:
         tile = p["bs"] * p["H"] * p["D"] * 2
         first_tile = buf[:tile].cpu().numpy().view(np.uint16).reshape(p["H"], p["bs"], p["D"])
         blk = int(sm[0]) // 16
@@ -505,5 +506,3 @@ def test_hnd_peer_pull_and_format_isolation():
     e_n.close()
     e_h.close()
     pool.close()
-    with pytest.raises(b200kv.B200KVError):
-        KVEngine(KVGeometry(L, H, D, NB, bs, 256, 2, 0, FMT_FP8, b200kv._lib.LAYOUT_HND), None, 0, staging_bytes=0)
