@@ -219,6 +219,11 @@ int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
  * touched.  Loads the longest prefix of chunks present in the pool, scatters into the
  * paged cache, and makes `compute_stream` wait for the scatter.  *n_loaded_tokens counts
  * tokens of chunks >= skip_chunks that were scheduled (the adapter's ret_token_mask.sum). */
+/* Pass as `compute_stream` to b200kv_load_async / b200kv_peer_pull_async for an ASYNCHRONOUS load
+ * (KVConnectorBase_V1.get_num_new_matched_tokens -> (n, is_async=True), base.py:453-486): no
+ * stream is made to wait; the caller polls the ticket and only then lets the request run.   */
+#define B200KV_STREAM_DETACHED ((void*)(intptr_t)-1)
+
 int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
                       const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
                       void* compute_stream, uint64_t* ticket, int64_t* n_loaded_tokens);

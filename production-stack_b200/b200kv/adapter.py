@@ -43,6 +43,7 @@ class ReqMeta:
     is_last_prefill: bool = False
     save_spec: SaveSpec | None = None
     load_spec: LoadSpec | None = None
+    async_load: bool = False     # load detached from the forward pass; completion reported by req id
 
     def slot_mapping(self, block_size: int) -> np.ndarray:
         b = np.asarray(self.block_ids, dtype=np.int64)
@@ -118,8 +119,15 @@ class SchedulerState:
     """Scheduler-role half.  `lookup(token_ids) -> hit tokens` is injected (pool index)."""
 
     def __init__(self, lookup, block_size: int, chunk: int, discard_partial_chunks: bool,
-                 save_decode_cache: bool = False, kv_role: str = "kv_both"):
+                 save_decode_cache: bool = False, kv_role: str = "kv_both", async_load: bool = False):
         self.lookup = lookup
+        # Asynchronous loads (KVConnectorBase_V1.get_num_new_matched_tokens -> (n, True)): the
+        # request waits in WAITING_FOR_REMOTE_KVS while its KV streams in, other requests keep
+        # running; vLLM itself recomputes the last token of a full hit
+        # (vllm/v1/core/sched/scheduler.py:2069-2101).
+        self.async_load = async_load
+        self._pending_async: list[ReqMeta] = []
+        self._async_saved: dict[str, int] = {}
         self.block_size = block_size
         self.chunk = chunk
         self.discard_partial_chunks = discard_partial_chunks
@@ -142,32 +150,42 @@ class SchedulerState:
         self.num_hit_tokens += hit
         self.num_requested_tokens += len(prompt_token_ids)
         need = hit - num_computed_tokens
-        if hit == num_tokens:
+        if hit == num_tokens and not self.async_load:
             need -= 1  # full-prompt hit: vLLM must still compute the last token
         self.load_specs[req_id] = LoadSpec(num_computed_tokens, hit, False)
         return max(need, 0)
 
     # update_state_after_alloc (adapter :1231-1293)
-    def after_alloc(self, request, num_external_tokens: int):
+    def after_alloc(self, request, num_external_tokens: int, block_ids=None):
         rid = request.request_id
         self.unfinished[rid] = request
         spec = self.load_specs.get(rid)
         if spec is None:
             return
         spec.can_load = num_external_tokens > 0
+        if self.async_load and spec.can_load:
+            # the request is not part of this step's SchedulerOutput: emit its load on its own
+            self.load_specs.pop(rid)
+            n = spec.external_cached_tokens
+            toks = (request.prompt_token_ids or [])[:n]
+            self._pending_async.append(ReqMeta(rid, np.asarray(toks, dtype=np.int32), first_group(block_ids),
+                                               load_spec=spec, async_load=True))
+            self._async_saved[rid] = n
 
     # build_connector_meta (adapter :1296-1407)
     def build_meta(self, scheduler_output) -> list[ReqMeta]:
-        out: list[ReqMeta] = []
+        out: list[ReqMeta] = self._pending_async
+        self._pending_async = []
         force_skip = self.kv_role == "kv_consumer"
         for rid in scheduler_output.finished_req_ids:
             self.trackers.pop(rid, None)
             self.unfinished.pop(rid, None)
             self.load_specs.pop(rid, None)
+            self._async_saved.pop(rid, None)
         for req in scheduler_output.scheduled_new_reqs:
             spec = self.load_specs.pop(req.req_id, None)
             n_compute = req.num_computed_tokens + scheduler_output.num_scheduled_tokens[req.req_id]
-            saved = spec.external_cached_tokens if spec is not None else 0
+            saved = spec.external_cached_tokens if spec is not None else self._async_saved.pop(req.req_id, 0)
             prompt = req.prompt_token_ids or []
             tr = RequestTracker(req.req_id, len(prompt), list(prompt[:n_compute]),
                                 first_group(req.block_ids), num_saved_tokens=saved, skip_save=force_skip)
@@ -218,6 +236,7 @@ class WorkerState:
         self.kv_role = kv_role
         self.load_error_blocks: set[int] = set()
         self.pending_tickets: list[int] = []
+        self.async_loads: list[tuple[int, str]] = []   # (ticket, req_id) of detached loads in flight
         self.stats = WorkerStats()
 
     def start_load(self, metas: list[ReqMeta], stream=None):
@@ -236,7 +255,11 @@ class WorkerState:
             masked = spec.vllm_cached_tokens // self.chunk * self.chunk
             mask[:masked] = False
             t0 = time.perf_counter()
-            ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
+            if m.async_load:
+                ret, ticket = self.engine.retrieve(tokens, mask, sm, stream="detached", return_ticket=True)
+                self.async_loads.append((ticket, m.req_id))
+            else:
+                ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
             self.stats.retrieve_seconds += time.perf_counter() - t0
             self.stats.retrieve_calls += 1
             got = int(ret.sum())
@@ -276,6 +299,17 @@ class WorkerState:
 
     def reap(self):
         self.pending_tickets = [t for t in self.pending_tickets if not self.engine.poll(t)]
+
+    def poll_async_loads(self) -> set[str]:
+        """Request ids whose detached load has landed (finished_recving of get_finished)."""
+        done, still = set(), []
+        for ticket, rid in self.async_loads:
+            if ticket == 0 or self.engine.poll(ticket):
+                done.add(rid)
+            else:
+                still.append((ticket, rid))
+        self.async_loads = still
+        return done
 
     def take_load_errors(self) -> set[int]:
         e, self.load_error_blocks = self.load_error_blocks, set()

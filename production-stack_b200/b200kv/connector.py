@@ -14,6 +14,7 @@ the POSIX-shm pool index (b200kv_pool): no ZMQ lookup server, no PYTHONHASHSEED 
 from __future__ import annotations
 
 import logging
+import os
 from dataclasses import dataclass, field
 from typing import TYPE_CHECKING, Any
 
@@ -36,6 +37,27 @@ if TYPE_CHECKING:
     from vllm.v1.request import Request
 
 logger = logging.getLogger("b200kv")
+
+_TRACE_PATH = os.environ.get("B200KV_TRACE")   # file to append per-call host timings to (debug only)
+
+
+def _traced(fn):
+    if not _TRACE_PATH:
+        return fn
+    import functools
+    import time as _t
+
+    @functools.wraps(fn)
+    def wrap(self, *a, **kw):
+        t0 = _t.perf_counter()
+        try:
+            return fn(self, *a, **kw)
+        finally:
+            dt = (_t.perf_counter() - t0) * 1e3
+            if dt > 0.05:
+                with open(_TRACE_PATH, "a") as f:
+                    f.write(f"{_t.time():.6f} {self._role.name} {fn.__name__} {dt:.3f} ms\n")
+    return wrap
 
 
 @dataclass
@@ -112,7 +134,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                 return pool.lookup_tokens(token_ids, chunk, seed, lease, include_partial)
 
             self._sched = SchedulerState(lookup, self._block_size, self._chunk, self._discard_partial,
-                                         self.cfg.save_decode_cache, self.kv_role)
+                                         self.cfg.save_decode_cache, self.kv_role, async_load=self.cfg.async_load)
         logger.info("b200kv connector role=%s kv_role=%s pool=%s (%.1f GB, chunk %d, fmt %s)",
                     role.name, self.kv_role, self._pool_name, self.cfg.max_local_cpu_size_gb, self._chunk,
                     "fp8" if self.cfg.fmt else "raw")
@@ -170,6 +192,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         assert isinstance(md, B200KVConnectorMetadata)
         return md.requests
 
+    @_traced
     def start_load_kv(self, forward_context: "ForwardContext", **kwargs: Any) -> None:
         if self._worker is None:
             return
@@ -185,19 +208,23 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
     def save_kv_layer(self, layer_name: str, kv_layer: torch.Tensor, attn_metadata, **kwargs: Any) -> None:
         return  # whole-request store in wait_for_save: CUDA-graph replay skips per-layer hooks (base.py:591-611)
 
+    @_traced
     def wait_for_save(self):
         if self._worker is None:
             return
         self._worker.save(self._metas(), stream=torch.cuda.current_stream())
 
+    @_traced
     def get_finished(self, finished_req_ids: set[str]) -> tuple[set[str] | None, set[str] | None]:
+        recv = None
         if self._worker is not None:
             self._worker.reap()
+            recv = self._worker.poll_async_loads() or None    # detached pool loads that have landed
+        sent = None
         if self._pdw is not None:
-            sent, _recv = self._pdw.poll()   # loads are synchronous for the scheduler: only sends are reported
-            if sent:
-                return sent, None
-        return None, None
+            sent, _pulled = self._pdw.poll()   # P/D pulls are synchronous for the scheduler
+            sent = sent or None
+        return sent, recv
 
     def get_block_ids_with_load_errors(self) -> set[int]:
         bad = self._worker.take_load_errors() if self._worker is not None else set()
@@ -206,6 +233,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         return bad
 
     # ------------------------------------------------------------------ stats (lmcache:* series)
+    @_traced
     def get_kv_connector_stats(self):
         """Worker side: deltas since the previous call (base.py:403)."""
         if self._worker is None or self._pool is None:
@@ -254,6 +282,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             self._pool = None
 
     # ------------------------------------------------------------------ scheduler side
+    @_traced
     def get_num_new_matched_tokens(self, request: "Request", num_computed_tokens: int) -> tuple[int | None, bool]:
         assert self._sched is not None and self._pd is not None
         remote = self._pd.remote_prefill_tokens(request, num_computed_tokens)
@@ -262,8 +291,9 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             return remote, False
         n = self._sched.num_new_matched_tokens(request.request_id, request.prompt_token_ids or [],
                                                request.num_tokens, num_computed_tokens)
-        return n, False
+        return n, bool(self._sched.async_load and n > 0)
 
+    @_traced
     def update_state_after_alloc(self, request: "Request", blocks: "KVCacheBlocks", num_external_tokens: int):
         assert self._sched is not None and self._pd is not None
         if request.request_id in self._remote_computed:
@@ -271,12 +301,15 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             self._pd.after_alloc(request, local, num_external_tokens, self._remote_computed.pop(request.request_id))
             self._sched.unfinished[request.request_id] = request
             return
-        self._sched.after_alloc(request, num_external_tokens)
+        self._sched.after_alloc(request, num_external_tokens,
+                                blocks.get_block_ids() if blocks is not None else None)
 
+    @_traced
     def build_connector_meta(self, scheduler_output: "SchedulerOutput") -> KVConnectorMetadata:
         assert self._sched is not None and self._pd is not None
         return B200KVConnectorMetadata(self._sched.build_meta(scheduler_output), self._pd.build_meta())
 
+    @_traced
     def request_finished(self, request: "Request", block_ids: list[int]) -> tuple[bool, dict[str, Any] | None]:
         # Offload: the gather that reads a request's pages is ordered before any later forward pass
         # on the compute stream, so blocks may be freed immediately.  Disaggregated prefill: keep

@@ -209,8 +209,13 @@ class KVPool:
             pass
 
 
+DETACHED = "detached"   # stream value for asynchronous loads (B200KV_STREAM_DETACHED)
+
+
 def _stream_ptr(stream) -> C.c_void_p:
-    """torch.cuda.Stream | int | None(-> current torch stream) -> cudaStream_t."""
+    """torch.cuda.Stream | int | None(-> current torch stream) | DETACHED -> cudaStream_t."""
+    if isinstance(stream, str) and stream == DETACHED:
+        return C.c_void_p(2 ** 64 - 1)
     if stream is None:
         import torch
         stream = torch.cuda.current_stream()

@@ -952,11 +952,14 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
   // (fatal for the engine), so the pins are dropped by the caller destroying the engine.
   CU_TRY(cudaEventCreateWithFlags(&op->done, cudaEventDisableTiming));
 
-  cudaEvent_t ev_compute;
-  CU_TRY(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
-  CU_TRY(cudaEventRecord(ev_compute, cs));
-  CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, ev_compute, 0));
-  CU_TRY(cudaEventDestroy(ev_compute));
+  const bool detached = compute_stream == B200KV_STREAM_DETACHED;
+  if (!detached) {
+    cudaEvent_t ev_compute;
+    CU_TRY(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(ev_compute, cs));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, ev_compute, 0));
+    CU_TRY(cudaEventDestroy(ev_compute));
+  }
 
   timing_reset(ctx, 1);
   const size_t n_stage = ctx->stage.size() - ctx->n_store_slots;
@@ -1021,7 +1024,7 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
   }
   CU_TRY(cudaLaunchHostFunc(ctx->s_scatter, op_host_cb, op.get()));
   CU_TRY(cudaEventRecord(op->done, ctx->s_scatter));
-  CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));  // the forward pass must see the loaded pages
+  if (!detached) CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));  // the forward pass must see the loaded pages
   ctx->stats.n_loaded_tokens += loaded;
   if (n_loaded_tokens) *n_loaded_tokens = loaded;
   *ticket = op->id;
@@ -1221,11 +1224,14 @@ extern "C" int b200kv_peer_pull_async(b200kv_ctx* ctx, int32_t peer_id, const in
   std::unique_ptr<Op> op(new Op());
   op->id = ctx->next_ticket++;
   CU_TRY(cudaEventCreateWithFlags(&op->done, cudaEventDisableTiming));
-  cudaEvent_t ev_compute;
-  CU_TRY(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
-  CU_TRY(cudaEventRecord(ev_compute, cs));
-  CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, ev_compute, 0));
-  CU_TRY(cudaEventDestroy(ev_compute));
+  const bool detached = compute_stream == B200KV_STREAM_DETACHED;
+  if (!detached) {
+    cudaEvent_t ev_compute;
+    CU_TRY(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(ev_compute, cs));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, ev_compute, 0));
+    CU_TRY(cudaEventDestroy(ev_compute));
+  }
   rc = table_upload(ctx, tv, ctx->s_scatter);
   if (rc) return rc;
 
@@ -1239,7 +1245,7 @@ extern "C" int b200kv_peer_pull_async(b200kv_ctx* ctx, int32_t peer_id, const in
   CU_TRY(cudaEventRecord(tv.slot->done_ev, ctx->s_scatter));
   CU_TRY(cudaLaunchHostFunc(ctx->s_scatter, op_host_cb, op.get()));
   CU_TRY(cudaEventRecord(op->done, ctx->s_scatter));
-  CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));
+  if (!detached) CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));
   ++ctx->stats.n_pull_ops;
   ctx->stats.n_pulled_tokens += n_tokens;
   ctx->stats.p2p_bytes += static_cast<uint64_t>(n_tokens) * ctx->g.token_bytes * ctx->g.planes;

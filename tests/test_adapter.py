@@ -25,12 +25,15 @@ class OracleBackedEngine:
         self.oe.store(tokens, mask, self.layers, slot_mapping, offset)
         return 1
 
-    def retrieve(self, tokens, mask, slot_mapping, stream=None):
-        self.calls.append(("retrieve", len(tokens), int((~mask).sum())))
-        return self.oe.retrieve(tokens, mask, self.layers, slot_mapping)
+    def retrieve(self, tokens, mask, slot_mapping, stream=None, return_ticket=False):
+        self.calls.append(("retrieve", len(tokens), int((~mask).sum()), stream))
+        ret = self.oe.retrieve(tokens, mask, self.layers, slot_mapping)
+        return (ret, 77) if return_ticket else ret
+
+    done = True
 
     def poll(self, t):
-        return True
+        return self.done
 
 
 def sched_out(new=(), cached=None, num_sched=None, finished=()):
@@ -103,7 +106,7 @@ def test_request_flow_miss_then_hit_with_last_token_rule():
     eng.calls.clear()
     before = [l.copy() for l in layers]
     worker.start_load(metas)
-    assert eng.calls == [("retrieve", len(prompt), 0)]
+    assert eng.calls == [("retrieve", len(prompt), 0, None)]
     sm_src = ko.slot_mapping_from_blocks(blocks, BS, len(prompt))
     sm_dst = ko.slot_mapping_from_blocks(blocks2, BS, len(prompt))
     assert np.array_equal(ko.gather_tokens(layers, sm_dst), ko.gather_tokens(before, sm_src))
@@ -120,7 +123,7 @@ def test_request_flow_miss_then_hit_with_last_token_rule():
                                        num_sched={"c": len(prompt3) - 2 * C}))
     eng.calls.clear()
     worker.start_load(metas)
-    assert eng.calls == [("retrieve", 2 * C, C)]                # first chunk masked (vLLM has it)
+    assert eng.calls == [("retrieve", 2 * C, C, None)]          # first chunk masked (vLLM has it)
     worker.save(metas)
     assert eng.calls[-1] == ("store", len(prompt3), 2 * C)      # only the new tail is stored
     assert sched.num_lookups == 3 and sched.num_hit_tokens == len(prompt) + 2 * C
@@ -169,3 +172,41 @@ def test_chunked_prefill_saves_whole_chunks_incrementally():
     # reference rule (adapter :313-316): once something is saved, a step that does not reach the
     # next chunk boundary saves nothing — even the last prefill's partial tail
     assert len(eng.calls) == 2
+
+
+def test_async_load_flow_request_waits_for_remote_kvs():
+    """B200KV_ASYNC_LOAD (default): get_num_new_matched_tokens -> (n, True); the load is emitted
+    for a request that is NOT in the SchedulerOutput, runs detached, is reported through
+    finished_recving, and the request is then scheduled as new with num_computed_tokens set
+    (vllm/v1/core/sched/scheduler.py:587-660, 763-781, 2069-2125)."""
+    rng = np.random.default_rng(3)
+    layers = [rng.integers(0, 2 ** 16, (2, 64, BS, 2, 8), dtype=np.uint16) for _ in range(2)]
+    eng = OracleBackedEngine(layers)
+    sched = SchedulerState(lambda t: eng.oe.lookup(t), BS, C, False, async_load=True)
+    worker = WorkerState(eng, BS, C)
+    prompt = list(rng.integers(0, 1000, 3 * C))                 # exactly 3 chunks
+    sm0 = ko.slot_mapping_from_blocks(list(range(12)), BS, len(prompt))
+    eng.oe.store(np.asarray(prompt, np.int32), np.ones(len(prompt), bool), layers, sm0)
+    req = NS(request_id="a", prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt)
+    need = sched.num_new_matched_tokens("a", prompt, len(prompt), 0)
+    assert need == len(prompt)                                  # full hit: vLLM drops the last token itself
+    blocks = (list(range(30, 42)),)
+    sched.after_alloc(req, need, blocks)                        # request goes to WAITING_FOR_REMOTE_KVS
+    metas = sched.build_meta(sched_out())                       # ... and is absent from the SchedulerOutput
+    assert len(metas) == 1 and metas[0].async_load and metas[0].save_spec is None
+    eng.calls.clear()
+    eng.done = False
+    worker.start_load(metas)
+    assert eng.calls == [("retrieve", len(prompt), 0, "detached")]
+    assert worker.poll_async_loads() == set()                   # still in flight
+    eng.done = True
+    assert worker.poll_async_loads() == {"a"}                   # -> finished_recving
+    sm1 = ko.slot_mapping_from_blocks(blocks[0], BS, len(prompt))
+    assert np.array_equal(ko.gather_tokens(layers, sm1), ko.gather_tokens(layers, sm0))
+    # second update_state_after_alloc (num_external_tokens = 0), then scheduled as a new request
+    sched.after_alloc(req, 0, blocks)
+    metas = sched.build_meta(sched_out([new_req("a", prompt, blocks[0], computed=len(prompt) - 1)], num_sched={"a": 1}))
+    eng.calls.clear()
+    worker.start_load(metas)
+    worker.save(metas)
+    assert eng.calls == []                                      # nothing to load again, nothing new to store

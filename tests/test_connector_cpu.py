@@ -41,6 +41,7 @@ def test_scheduler_role_lookup_and_metadata(monkeypatch):
     from b200kv.connector import B200KVConnector, B200KVConnectorMetadata, geometry_from_vllm
     monkeypatch.setenv("LMCACHE_MAX_LOCAL_CPU_SIZE", "0.05")
     monkeypatch.setenv("LMCACHE_CHUNK_SIZE", "64")
+    monkeypatch.setenv("B200KV_ASYNC_LOAD", "0")        # the synchronous (LMCache-like) flow; async: test_adapter.py
     eid = f"t{os.getpid()}x{os.urandom(3).hex()}"
     cfg = fake_vllm_config(eid)
     conn = B200KVConnector(cfg, KVConnectorRole.SCHEDULER, None)
