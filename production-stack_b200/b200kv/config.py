@@ -41,7 +41,8 @@ class B200KVConfig:
     staging_mb: int = 1024                # B200KV_STAGING_MB: device staging ring
     lookup_lease_ms: int = 30000          # B200KV_LOOKUP_LEASE_MS
     variant: int = 0                      # B200KV_VARIANT (0 bulk/TMA, 1 LDG)
-    async_load: bool = True               # B200KV_ASYNC_LOAD: loads detached from the forward pass
+    async_load: bool = False              # B200KV_ASYNC_LOAD=1: loads detached from the forward pass (measured
+                                          # slower on this workload: +1 scheduler step; profiles/e2e_mrqa_r01.json)
     extra: dict = field(default_factory=dict)
 
     @staticmethod
@@ -67,7 +68,7 @@ class B200KVConfig:
         c.staging_mb = int(e.get("B200KV_STAGING_MB", c.staging_mb))
         c.lookup_lease_ms = int(e.get("B200KV_LOOKUP_LEASE_MS", c.lookup_lease_ms))
         c.variant = int(e.get("B200KV_VARIANT", 0))
-        c.async_load = _b(e.get("B200KV_ASYNC_LOAD"), True)
+        c.async_load = _b(e.get("B200KV_ASYNC_LOAD"), False)
         for k in _IGNORED:
             if e.get(k) not in (None, "", "0", "False", "false"):
                 logger.warning("%s=%s is accepted for chart compatibility but has no effect in b200kv", k, e.get(k))
