@@ -118,13 +118,18 @@ def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024):
              ko.slot_mapping_from_blocks(dperm[s * nblk:(s + 1) * nblk], BS, CTX)) for s in range(sessions)]
     threads = oracle_c.lib().oracle_num_threads()
     keys_out = np.zeros(CTX // C, dtype=np.uint64)
+    lib = oracle_c.lib()
+    planes, stride = oracle_c.planes_of(layers)
+    cb = 2 * L * C * H * D * 2
+    pool = np.zeros(sessions * (CTX // C) * cb, dtype=np.uint8)   # the "CPU pool": reused every step
 
     def one_step(step):
         for s, (sm, dm) in enumerate(maps):
             toks = session_tokens(0, step, s)
-            oracle_c.lib().oracle_chunk_keys(toks.ctypes.data, CTX, C, 0, 1, keys_out.ctypes.data)
-            chunks, cb, so = oracle_c.gather(layers, sm, C, "raw")
-            oracle_c.scatter(layers, dm, C, chunks, cb, so, "raw")
+            lib.oracle_chunk_keys(toks.ctypes.data, CTX, C, 0, 1, keys_out.ctypes.data)
+            slot = pool[s * (CTX // C) * cb:]
+            lib.oracle_gather_raw(planes, 2 * L, stride, BS, H * D * 2, sm.ctypes.data, CTX, C, slot.ctypes.data, cb)
+            lib.oracle_scatter_raw(planes, 2 * L, stride, BS, H * D * 2, dm.ctypes.data, CTX, C, slot.ctypes.data, cb)
 
     for w in range(warmup):
         one_step(w)
@@ -243,11 +248,11 @@ def run_ours(args):
             n += int(eng.retrieve(toks[s], None, dst_maps[s], stream=stream).sum())
         return n
 
+    sampler = ClockSampler(local) if rank == 0 else None   # nvidia-smi needs ~1 s to start emitting
     for w in range(args.warmup):
         assert e2e_step(w) == SESSIONS * CTX
     torch.cuda.synchronize()
     st0 = eng.stats()
-    sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)

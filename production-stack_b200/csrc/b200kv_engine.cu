@@ -186,6 +186,7 @@ struct b200kv_ctx {
 
   // bulk-kernel launch shape
   int S = 2, LAG = 1, ctas_per_sm = 1;  // swept on B200: profiles/sweep_r01.txt
+  int fp8_threads = 256;                // B200KV_FP8_THREADS: CTA width of the FP8 store kernel
   uint32_t piece_tokens = 0, pieces = 0, stage_bytes = 0;
 };
 
@@ -466,16 +467,17 @@ int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView&
   p.hnd = ctx->g.hnd ? 1u : 0u;
   const size_t smem = static_cast<size_t>(ctx->g.C / kCluster) * ctx->g.token_bytes;
   if (smem > 200 * 1024) return B200KV_ENOTSUP;
+  const uint32_t grid = kCluster * n_chunks * ctx->g.planes;
+  if (grid == 0) return B200KV_OK;
   static bool attr_set[8] = {false};
   const int dev = ctx->cfg.device & 7;
   if (!attr_set[dev]) {
-    CU_TRY(cudaFuncSetAttribute(kv_fp8_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                200 * 1024));
+    CU_TRY(cudaFuncSetAttribute(kv_fp8_store_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU_TRY(cudaFuncSetAttribute(kv_fp8_store_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev] = true;
   }
-  const uint32_t grid = kCluster * n_chunks * ctx->g.planes;
-  if (grid == 0) return B200KV_OK;
-  kv_fp8_store_kernel<<<grid, kFp8Threads, smem, s>>>(p);
+  if (ctx->fp8_threads == 512) kv_fp8_store_kernel<512><<<grid, 512, smem, s>>>(p);
+  else kv_fp8_store_kernel<256><<<grid, 256, smem, s>>>(p);
   CU_TRY(cudaGetLastError());
   ++ctx->stats.n_kernel_launches;
   return B200KV_OK;
@@ -618,6 +620,7 @@ extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool
   ctx->S = cfg->stages > 0 ? cfg->stages : env_int("B200KV_STAGES", 2);
   ctx->LAG = env_int("B200KV_LAG", ctx->S / 2);
   ctx->ctas_per_sm = cfg->ctas_per_sm > 0 ? cfg->ctas_per_sm : env_int("B200KV_CTAS_PER_SM", 1);
+  ctx->fp8_threads = env_int("B200KV_FP8_THREADS", 256) == 512 ? 512 : 256;
   const uint32_t stage_max = static_cast<uint32_t>(env_int("B200KV_STAGE_KB", 32)) << 10;
   if (g.token_bytes > stage_max || stage_max > kStageMax * 2) return B200KV_ENOTSUP;
   ctx->piece_tokens = std::min<uint32_t>(g.bs, stage_max / g.token_bytes);

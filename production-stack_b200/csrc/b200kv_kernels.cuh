@@ -378,7 +378,8 @@ __device__ __forceinline__ uint2 quant8(const uint4& v, float inv) {
   return make_uint2(o[0], o[1]);
 }
 
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
+template <int kThreads>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     kv_fp8_store_kernel(const Fp8StoreParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -446,7 +447,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
   const uint32_t tile_rows = p.paged.block_tokens * rv;  // vectors per (tile, head)
   const uint32_t hnd_total = (W / p.paged.block_tokens) * p.n_heads * tile_rows;
   if (p.hnd) {
-    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kFp8Threads) {
+    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kThreads) {
       const uint32_t rowi = (idx / rv) % p.paged.block_tokens;
       const uint32_t h = (idx / tile_rows) % p.n_heads;
       const uint32_t tile = idx / (tile_rows * p.n_heads);
@@ -461,10 +462,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
   } else {
   // ---- per-head absmax over this CTA's tokens: a thread's 16-byte column has a fixed head ----
     // When a token has fewer than 256 vectors the spare threads split the tokens between them.
-    const uint32_t groups = vpt < kFp8Threads ? kFp8Threads / vpt : 1;
+    const uint32_t groups = vpt < kThreads ? kThreads / vpt : 1;
     const uint32_t grp = threadIdx.x / vpt;
     if (grp < groups) {
-      const uint32_t col_step = groups == 1 ? kFp8Threads : vpt;
+      const uint32_t col_step = groups == 1 ? kThreads : vpt;
       for (uint32_t col = threadIdx.x - grp * vpt; col < vpt; col += col_step) {
         uint32_t acc = 0;
         const uint8_t* q = smem + static_cast<size_t>(col) * 16;
@@ -498,7 +499,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
     // the packed slab mirrors the tiles at half size: same vector index, 8 bytes each
     uint8_t* outh = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
                                                static_cast<uint64_t>(rank * W) * (tb >> 1));
-    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kFp8Threads) {
+    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kThreads) {
       const uint32_t rowi = (idx / rv) % p.paged.block_tokens;
       const uint32_t h = (idx / tile_rows) % p.n_heads;
       const uint32_t tile = idx / (tile_rows * p.n_heads);
@@ -513,15 +514,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFp8Threads)
   uint8_t* out = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
                                             static_cast<uint64_t>(rank * W) * (tb >> 1));
   const uint32_t nvec = n_valid * vpt;
-  if ((kFp8Threads % vpt) == 0) {
+  if ((kThreads % vpt) == 0) {
     // i % vpt == threadIdx.x % vpt for every i of this thread: one head, one scale, no division
     const float inv = s_inv[((threadIdx.x % vpt) * 16) / p.head_bytes];
-    for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+    for (uint32_t i = threadIdx.x; i < nvec; i += kThreads) {
       const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(i) * 16);
       st_na_v2(out + static_cast<size_t>(i) * 8, quant8(v, inv));
     }
   } else {
-    for (uint32_t i = threadIdx.x; i < nvec; i += kFp8Threads) {
+    for (uint32_t i = threadIdx.x; i < nvec; i += kThreads) {
       const uint32_t col = i % vpt;
       const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(i) * 16);
       st_na_v2(out + static_cast<size_t>(i) * 8, quant8(v, s_inv[(col * 16) / p.head_bytes]));

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import asyncio
+import hashlib
 import json
 import statistics
 import time
@@ -90,8 +91,9 @@ async def user_session(session, args, uid, start_delay, rows):
         except Exception as e:  # a failed request is recorded, not fatal (the harness logs and goes on)
             rows.append({"user_id": uid, "question_id": k, "error": repr(e)})
             return
-        history.append({"role": "assistant", "content": res.pop("body")})
-        res.update(user_id=uid, question_id=k)
+        body = res.pop("body")
+        history.append({"role": "assistant", "content": body})
+        res.update(user_id=uid, question_id=k, body_sha1=hashlib.sha1(body.encode()).hexdigest()[:16])
         rows.append(res)
         wait = gap - (time.time() - t_launch)
         if wait > 0 and k < args.num_rounds:
