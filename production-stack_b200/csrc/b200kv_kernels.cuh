@@ -15,10 +15,12 @@
 //                        S-stage ring, then cp.async.bulk smem->global (bulk_group).  No
 //                        registers touch the payload.  Persistent grid.
 //   kv_ldg_copy_kernel   same contract with 128-bit ld.global.nc / st.global (A/B variant).
-//   kv_fp8_store_kernel  cluster of 8 CTAs per (chunk, layer, K/V) slab: bulk-load 32 tokens
-//                        each into smem, per-head absmax in registers -> smem -> DSMEM exchange
-//                        across the cluster, quantise to e4m3 from smem, coalesced store.  HBM
-//                        is read exactly once.
+//   kv_fp8_store_kernel  cluster of 8 CTAs per (chunk, layer, K/V) slab: warp 0 bulk-loads the CTA's 32
+//                        tokens into smem (one run per lane), per-head absmax in registers -> smem,
+//                        every CTA pushes its maxima into all 8 CTAs' smem with DSMEM atomics
+//                        (red.shared::cluster.max) between a split cluster barrier (arrive early,
+//                        wait late) and one full one, quantise to e4m3 from smem, coalesced stores.
+//                        HBM is read exactly once.  NHD and HND tiles.
 //   kv_fp8_load_kernel   bulk-load e4m3 piece -> dequantise -> 16-byte stores into the pages.
 #pragma once
 
@@ -149,6 +151,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
                    : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// atomic max into the same shared variable of CTA `rank` of this cluster (DSMEM)
+__device__ __forceinline__ void red_dsmem_max_u32(void* local_smem_ptr, uint32_t rank, uint32_t v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+  asm volatile("red.relaxed.cluster.shared::cluster.max.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_dsmem_u32(const void* local_smem_ptr, uint32_t rank) {
   uint32_t remote, v;
@@ -383,7 +397,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     kv_fp8_store_kernel(const Fp8StoreParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t s_absmax[kMaxHeads];  // bf16 |x| bits (integer order == magnitude order)
+  __shared__ uint32_t s_absmax[kMaxHeads];  // this CTA's |x| max per head (bf16 bits: integer order == magnitude)
+  __shared__ uint32_t s_all[kMaxHeads];     // cluster-wide max: every CTA pushes its value into every CTA's copy
   __shared__ float s_inv[kMaxHeads];
 
   const uint32_t rank = cluster_ctarank();
@@ -398,7 +413,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
   const uint32_t chunk_hi = min((c + 1) * p.chunk_tokens, p.n_tokens);
   if (win_lo + n_valid > chunk_hi) n_valid = chunk_hi > win_lo ? chunk_hi - win_lo : 0;
 
-  if (threadIdx.x < kMaxHeads) s_absmax[threadIdx.x] = 0;
+  if (threadIdx.x < kMaxHeads) {
+    s_absmax[threadIdx.x] = 0;
+    s_all[threadIdx.x] = 0;
+  }
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -438,6 +456,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     // complete_tx may land before this expect_tx: the phase cannot complete until the arrive
     if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, total);
   }
+  // Cluster barrier #1, split: arrive now (publishes the zeroed s_all), wait only just before the
+  // DSMEM pushes — its latency hides behind the bulk loads that are already in flight.
+  cluster_arrive_release();
   mbar_wait(&bar, 0);
 
   const uint32_t vpt = tb >> 4;  // 16-byte vectors per token
@@ -479,12 +500,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     }
   }
   __syncthreads();
-  cluster_sync_all();  // every CTA's s_absmax is final and visible cluster-wide
+  cluster_wait_acquire();  // #1: every CTA of the cluster has zeroed its s_all
+  if (threadIdx.x < p.n_heads) {
+    const uint32_t mine = s_absmax[threadIdx.x];
+#pragma unroll
+    for (uint32_t r = 0; r < kCluster; ++r) red_dsmem_max_u32(&s_all[threadIdx.x], r, mine);
+  }
+  // Cluster barrier #2: all pushes have landed everywhere.  Nothing remote is touched after it, so
+  // no trailing barrier is needed to keep shared memory alive.
+  cluster_arrive_release();
+  cluster_wait_acquire();
 
   if (threadIdx.x < p.n_heads) {
-    uint32_t m = 0;
-#pragma unroll
-    for (uint32_t r = 0; r < kCluster; ++r) m = max(m, ld_dsmem_u32(&s_absmax[threadIdx.x], r));
+    const uint32_t m = s_all[threadIdx.x];
     const float amax = __uint_as_float(m << 16);
     const float inv = (m == 0) ? 1.0f : __fdiv_rn(448.0f, amax);
     s_inv[threadIdx.x] = inv;
@@ -507,9 +535,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
       const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(idx) * 16);
       st_na_v2(outh + static_cast<size_t>(idx) * 8, quant8(v, s_inv[h]));
     }
-    cluster_sync_all();
     return;
   }
+
   // ---- quantise from smem, 8-byte coalesced stores ----
   uint8_t* out = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
                                             static_cast<uint64_t>(rank * W) * (tb >> 1));
@@ -528,7 +556,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
       st_na_v2(out + static_cast<size_t>(i) * 8, quant8(v, s_inv[(col * 16) / p.head_bytes]));
     }
   }
-  cluster_sync_all();  // keep smem alive until every peer CTA has read our s_absmax
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,54 @@
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "production-stack_b200")]
+import b200kv
+from b200kv import FMT_FP8, KVEngine, KVGeometry
+from oracle import kv_oracle as ko
+L, NB, bs, H, D, C = 2, 32, 16, 8, 128, 256
+rng = np.random.default_rng(0)
+host = []
+for _ in range(L):
+    x = rng.standard_normal((2, NB, bs, H, D)).astype(np.float32) * np.exp(rng.uniform(-3, 3, (2, 1, 1, H, 1))).astype(np.float32)
+    host.append(ko.f32_to_bf16_bits_rn(x).reshape(2, NB, bs, H, D))
+def to_dev_hnd(layers):
+    out = []
+    for l in layers:
+        t = torch.from_numpy(l.view(np.int16)).view(torch.bfloat16).cuda()
+        out.append(t.permute(1, 0, 3, 2, 4).contiguous().permute(0, 1, 3, 2, 4))
+    return out
+for n_tok in (1, 16, 40):
+    dev = to_dev_hnd(host)
+    geom = KVGeometry(L, H, D, NB, bs, C, 2, 2 * bs * H * D * 2, FMT_FP8, 1)
+    eng = KVEngine(geom, None, 0, staging_bytes=0)
+    eng.register_kv_caches(dev)
+    sm = ko.slot_mapping_from_blocks(rng.permutation(NB)[: (n_tok + 15) // 16], 16, n_tok)
+    buf = torch.zeros(geom.chunk_bytes, dtype=torch.uint8, device="cuda")
+    eng.gather(sm, buf.data_ptr())
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy()
+    bits = ko.gather_tokens(host, sm)                  # (L,2,n,H,D)
+    codes, scales = ko.fp8_pack_chunk(bits)
+    so = 2 * L * C * H * D
+    gs = got[so:so + 2 * L * H * 4].view(np.float32).reshape(L, 2, H)
+    print("n_tok", n_tok, "scales equal", np.array_equal(gs, scales), "max rel diff", np.abs(gs / scales - 1).max())
+    bad = 0
+    for l in range(L):
+        for kv in range(2):
+            slab = got[(l * 2 + kv) * C * H * D:(l * 2 + kv + 1) * C * H * D]
+            for t in range(n_tok):
+                tile, row = t // 16, t % 16
+                for h in range(H):
+                    o = tile * 16 * H * D + h * 16 * D + row * D
+                    if not np.array_equal(slab[o:o + D], codes[l, kv, t, h]):
+                        if bad < 5:
+                            print("  code mismatch l", l, "kv", kv, "t", t, "h", h, slab[o:o + 8], codes[l, kv, t, h][:8])
+                        bad += 1
+    print("  code mismatches", bad, "of", L * 2 * n_tok * H)
+    for t in dev: t.zero_()
+    eng.scatter(sm, buf.data_ptr())
+    torch.cuda.synchronize()
+    want = ko.fp8_unpack_chunk(codes, scales)
+    gotb = ko.gather_tokens([d.permute(1, 0, 2, 3, 4).contiguous().cpu().view(torch.int16).numpy().view(np.uint16) for d in dev], sm)
+    print("  scatter equal", np.array_equal(gotb, want), "n diff", int((gotb != want).sum()))
+    eng.close()
