@@ -578,10 +578,25 @@ extern "C" int64_t b200kv_engine_chunk_bytes(const b200kv_engine_config* cfg) {
   return static_cast<int64_t>(g.chunk_bytes);
 }
 
+static int engine_create_impl(const b200kv_engine_config* cfg, b200kv_pool* pool, b200kv_ctx** out);
+
+extern "C" int b200kv_engine_destroy(b200kv_ctx* ctx);
+
 extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool* pool,
                                     b200kv_ctx** out) {
   if (!cfg || !out) return B200KV_EINVAL;
   *out = nullptr;
+  b200kv_ctx* ctx = nullptr;
+  const int rc = engine_create_impl(cfg, pool, &ctx);
+  if (rc != B200KV_OK) {
+    if (ctx) b200kv_engine_destroy(ctx);  // releases whatever had been created (streams, buffers, pinning)
+    return rc;
+  }
+  *out = ctx;
+  return B200KV_OK;
+}
+
+static int engine_create_impl(const b200kv_engine_config* cfg, b200kv_pool* pool, b200kv_ctx** out) {
   Geometry g;
   int rc = make_geometry(cfg, &g);
   if (rc) return rc;
@@ -609,8 +624,9 @@ extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool
     return B200KV_ENOTSUP;
   }
 
-  std::unique_ptr<b200kv_ctx> ctx(new (std::nothrow) b200kv_ctx());
+  b200kv_ctx* ctx = new (std::nothrow) b200kv_ctx();
   if (!ctx) return B200KV_ENOMEM;
+  *out = ctx;  // from here on the caller destroys it on failure
   ctx->cfg = *cfg;
   ctx->g = g;
   ctx->pool = pool;
@@ -675,7 +691,6 @@ extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool
       return B200KV_ENODEV;
     }
   }
-  *out = ctx.release();
   return B200KV_OK;
 }
 
@@ -820,6 +835,13 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
   cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
   *ticket = 0;
 
+  // 0. validate every slot BEFORE touching the pool: a malformed mapping must not leave chunks
+  //    reserved-but-never-committed
+  {
+    const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
+    for (int64_t i = 0; i < n_tokens; ++i)
+      if (slot_mapping[i] < 0 || slot_mapping[i] >= max_slot) return B200KV_EINVAL;
+  }
   // 1. reserve pool slots; chunks already present (or not placeable) are skipped
   struct Todo { int32_t c; uint32_t slot; uint32_t n_tok; };
   std::vector<Todo> todo;
@@ -930,6 +952,11 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
   cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
   *ticket = 0;
   if (n_loaded_tokens) *n_loaded_tokens = 0;
+  {
+    const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
+    for (int64_t i = 0; i < n_tokens; ++i)
+      if (slot_mapping[i] < 0 || slot_mapping[i] >= max_slot) return B200KV_EINVAL;  // before pinning anything
+  }
 
   struct Todo { int32_t c; uint32_t slot; uint32_t n_tok; };
   std::vector<Todo> todo;
