@@ -115,6 +115,14 @@ def make_req_meta(tracker: RequestTracker, block_size: int, chunk: int, load_spe
                    load_spec=load_spec)
 
 
+def request_skip_save(req) -> bool:
+    """Per-request opt-out `kv_transfer_params["lmcache.skip_save"]` (adapter :102-117, :311)."""
+    sp = getattr(req, "sampling_params", None)
+    extra = getattr(sp, "extra_args", None) or {}
+    ktp = extra.get("kv_transfer_params") or {}
+    return bool(ktp.get("lmcache.skip_save") or ktp.get("b200kv.skip_save"))
+
+
 class SchedulerState:
     """Scheduler-role half.  `lookup(token_ids) -> hit tokens` is injected (pool index)."""
 
@@ -188,7 +196,8 @@ class SchedulerState:
             saved = spec.external_cached_tokens if spec is not None else self._async_saved.pop(req.req_id, 0)
             prompt = req.prompt_token_ids or []
             tr = RequestTracker(req.req_id, len(prompt), list(prompt[:n_compute]),
-                                first_group(req.block_ids), num_saved_tokens=saved, skip_save=force_skip)
+                                first_group(req.block_ids), num_saved_tokens=saved,
+                                skip_save=force_skip or request_skip_save(req))
             self.trackers[req.req_id] = tr
             m = make_req_meta(tr, self.block_size, self.chunk, spec, self.discard_partial_chunks,
                               self.save_decode_cache)

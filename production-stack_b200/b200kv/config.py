@@ -46,8 +46,20 @@ class B200KVConfig:
     extra: dict = field(default_factory=dict)
 
     @staticmethod
+    def _file_overrides(path: str) -> dict:
+        """LMCACHE_CONFIG_FILE: LMCache's YAML config (vllm/.../lmcache_integration/utils.py:47-62);
+        its keys are the env names without the LMCACHE_ prefix, lower-cased."""
+        import yaml
+        with open(path) as f:
+            doc = yaml.safe_load(f) or {}
+        return {"LMCACHE_" + str(k).upper(): str(v) for k, v in doc.items() if v is not None}
+
+    @staticmethod
     def from_env(env=None) -> "B200KVConfig":
-        e = os.environ if env is None else env
+        e = dict(os.environ if env is None else env)
+        if e.get("LMCACHE_CONFIG_FILE"):
+            # file first, explicit environment variables win
+            e = {**B200KVConfig._file_overrides(e["LMCACHE_CONFIG_FILE"]), **e}
         c = B200KVConfig()
         c.chunk_size = int(e.get("LMCACHE_CHUNK_SIZE", c.chunk_size))
         c.local_cpu = _b(e.get("LMCACHE_LOCAL_CPU"), True)

@@ -138,3 +138,21 @@ def test_lmcache_prometheus_series_names_and_aggregation():
                    "lmcache:retrieve_speed_sum", "lmcache:retrieve_speed_count"):
         assert series in text, series
     assert 'lmcache:num_hit_tokens_total{engine="0",model_name="synth"} 520.0' in text
+
+
+def test_config_file_and_per_request_skip_save(tmp_path):
+    from types import SimpleNamespace as NS
+
+    from b200kv.adapter import SchedulerState, request_skip_save
+    from b200kv.config import B200KVConfig
+    f = tmp_path / "lmcache.yaml"
+    f.write_text("chunk_size: 128\nlocal_cpu: true\nmax_local_cpu_size: 12\nremote_serde: cachegen\n")
+    c = B200KVConfig.from_env({"LMCACHE_CONFIG_FILE": str(f), "LMCACHE_MAX_LOCAL_CPU_SIZE": "40"})
+    assert c.chunk_size == 128 and c.fmt == 1 and c.max_local_cpu_size_gb == 40.0     # env beats file
+    req = NS(req_id="r", prompt_token_ids=list(range(300)), block_ids=([1] * 19,), num_computed_tokens=0,
+             sampling_params=NS(extra_args={"kv_transfer_params": {"lmcache.skip_save": True}}))
+    assert request_skip_save(req)
+    sched = SchedulerState(lambda t: 0, 16, 256, False)
+    out = NS(scheduled_new_reqs=[req], scheduled_cached_reqs=NS(req_ids=[], new_block_ids=[], resumed_req_ids=set(), all_token_ids={}),
+             num_scheduled_tokens={"r": 300}, finished_req_ids=set())
+    assert sched.build_meta(out) == []                                                 # nothing saved, nothing loaded
