@@ -234,6 +234,17 @@ def test_bad_arguments_are_errors_not_crashes():
         eng.gather(np.array([-1]), buf.data_ptr())
     with pytest.raises(b200kv.B200KVError):
         eng.store(np.arange(16), None, np.arange(16))       # no pool attached
+    # an op whose run table would not fit the 1 MiB table slot is refused, not truncated
+    # (token-granular mapping: one 12-byte run per token)
+    big = KVEngine(KVGeometry(2, 4, 64, 8192, 16, 64), None, 0, staging_bytes=0)
+    bdev = [torch.zeros((2, 8192, 16, 4, 64), dtype=torch.bfloat16, device="cuda:0") for _ in range(2)]
+    big.register_kv_caches(bdev)
+    n_big = 100_000
+    bbuf = torch.zeros(((n_big + 63) // 64) * big.geom.chunk_bytes, dtype=torch.uint8, device="cuda:0")
+    with pytest.raises(b200kv.B200KVError) as ei:
+        big.gather((np.arange(n_big, dtype=np.int64) * 7) % (8192 * 16), bbuf.data_ptr())
+    assert ei.value.code == b200kv._lib.EINVAL
+    big.close()
     hnd = [t.permute(0, 1, 3, 2, 4).contiguous().permute(0, 1, 3, 2, 4) for t in dev]
     with pytest.raises(ValueError):
         eng.register_kv_caches(hnd)                          # HND tensors on an engine built for NHD
