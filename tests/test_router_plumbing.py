@@ -165,7 +165,14 @@ def test_config4_kvaware_routes_to_the_instance_holding_the_kv(tmp_path, shm_nam
                     pool.commit(int(k))
             clients.append(ControllerClient(f"127.0.0.1:{cport}", f"pod-{i}", f"{shm_name}-{i}", 77, 256,
                                             heartbeat_s=0.5, ip=h))
-        time.sleep(2.0)   # registrations reach the in-router controller
+        # registrations travel over ZMQ to the in-router controller: wait until routing reflects them
+        deadline = time.time() + 30
+        while time.time() < deadline:
+            st, body = post(f"http://127.0.0.1:{rport}/v1/completions",
+                            {"model": model_dir, "prompt": prompt, "max_tokens": 1}, {"x-user-id": "probe"})
+            if st == 200 and body.get("served_by") == "127.0.0.2":
+                break
+            time.sleep(0.5)
         hit_hosts = []
         for i in range(6):
             st, body = post(f"http://127.0.0.1:{rport}/v1/completions",
