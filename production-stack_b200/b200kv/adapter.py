@@ -17,9 +17,12 @@ across the scheduler->worker boundary); the slot mapping slot[i] = block[i//bs]*
 """
 from __future__ import annotations
 
+import logging
 from dataclasses import dataclass, field
 
 import numpy as np
+
+logger = logging.getLogger("b200kv")
 
 
 @dataclass
@@ -264,11 +267,17 @@ class WorkerState:
             masked = spec.vllm_cached_tokens // self.chunk * self.chunk
             mask[:masked] = False
             t0 = time.perf_counter()
-            if m.async_load:
-                ret, ticket = self.engine.retrieve(tokens, mask, sm, stream="detached", return_ticket=True)
-                self.async_loads.append((ticket, m.req_id))
-            else:
-                ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
+            try:
+                if m.async_load:
+                    ret, ticket = self.engine.retrieve(tokens, mask, sm, stream="detached", return_ticket=True)
+                    self.async_loads.append((ticket, m.req_id))
+                else:
+                    ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
+            except Exception as e:  # no exception on the data path (SURVEY §8b "Errors"): recompute instead
+                logger.error("b200kv: retrieve failed for %s: %s", m.req_id, e)
+                ret = np.zeros(n, dtype=bool)
+                if m.async_load:
+                    self.async_loads.append((0, m.req_id))   # still has to be reported as finished
             self.stats.retrieve_seconds += time.perf_counter() - t0
             self.stats.retrieve_calls += 1
             got = int(ret.sum())
@@ -300,7 +309,11 @@ class WorkerState:
             sm = m.slot_mapping(self.block_size)[:n]
             mask = np.ones(n, dtype=bool)
             mask[:lead] = False
-            ticket = self.engine.store(tokens[:n], mask, sm, offset=lead, stream=stream)
+            try:
+                ticket = self.engine.store(tokens[:n], mask, sm, offset=lead, stream=stream)
+            except Exception as e:  # a failed store is a future miss, never a failed request
+                logger.error("b200kv: store failed for %s: %s", m.req_id, e)
+                continue
             if ticket:
                 self.pending_tickets.append(ticket)
             self.stats.num_stored_tokens += n - lead

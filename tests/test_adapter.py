@@ -210,3 +210,26 @@ def test_async_load_flow_request_waits_for_remote_kvs():
     worker.start_load(metas)
     worker.save(metas)
     assert eng.calls == []                                      # nothing to load again, nothing new to store
+
+
+def test_engine_failures_never_raise_on_the_data_path():
+    """SURVEY §8b "Errors": a failed load becomes load-error blocks (vLLM recomputes), a failed store
+    becomes a future miss."""
+    from b200kv.adapter import SaveSpec
+
+    class Broken(OracleBackedEngine):
+        def retrieve(self, *a, **k):
+            raise RuntimeError("cuda went away")
+
+        def store(self, *a, **k):
+            raise RuntimeError("pool is gone")
+
+    w = WorkerState(Broken([np.zeros((2, 8, BS, 1, 8), np.uint16)]), BS, C)
+    m = ReqMeta("x", np.arange(2 * C, dtype=np.int32), list(range(50, 58)), True, SaveSpec(0, True), LoadSpec(0, 2 * C, True))
+    w.start_load([m])
+    assert w.take_load_errors() == set(range(50, 58))
+    w.save([m])                                   # logged, skipped
+    assert w.pending_tickets == []
+    a = ReqMeta("y", np.arange(C, dtype=np.int32), [1, 2, 3, 4], load_spec=LoadSpec(0, C, True), async_load=True)
+    w.start_load([a])
+    assert w.poll_async_loads() == {"y"} and w.take_load_errors() == {1, 2, 3, 4}
