@@ -228,6 +228,19 @@ int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
                       const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
                       void* compute_stream, uint64_t* ticket, int64_t* n_loaded_tokens);
 
+/* Layer-wise retrieve (LMCache `use_layerwise`: lmcache_engine.retrieve_layer, adapter :870-880;
+ * KVConnectorBase_V1.wait_for_layer_load, base.py:310-322).  Same arguments as b200kv_load_async,
+ * but the H2D copies and scatters are issued per group of `layers_per_group` layers across all
+ * chunks, group 0 first; `compute_stream` is NOT made to wait for the whole load.  Instead the
+ * caller calls b200kv_wait_layer(ticket, layer, stream) before the attention of `layer` runs: the
+ * PCIe transfer of later layers overlaps the forward pass of earlier ones.  Falls back to one
+ * whole-op wait if the op does not fit the load half of the staging ring.                  */
+int b200kv_load_layerwise_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
+                                const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
+                                int32_t layers_per_group, void* compute_stream, uint64_t* ticket,
+                                int64_t* n_loaded_tokens);
+int b200kv_wait_layer(b200kv_ctx* ctx, uint64_t ticket, int32_t layer, void* compute_stream);
+
 int b200kv_poll(b200kv_ctx* ctx, uint64_t ticket, int* done);
 int b200kv_wait(b200kv_ctx* ctx, uint64_t ticket);
 int b200kv_wait_all(b200kv_ctx* ctx);

@@ -249,11 +249,16 @@ class WorkerState:
         self.load_error_blocks: set[int] = set()
         self.pending_tickets: list[int] = []
         self.async_loads: list[tuple[int, str]] = []   # (ticket, req_id) of detached loads in flight
+        # layer-wise loads of the current step: (ticket, blocks it fills); the forward pass waits per layer
+        self.layer_loads: list[tuple[int, list[int]]] = []
         self.stats = WorkerStats()
 
-    def start_load(self, metas: list[ReqMeta], stream=None):
-        """start_load_kv (adapter :798-905)."""
+    def start_load(self, metas: list[ReqMeta], stream=None, layers_per_group: int = 0):
+        """start_load_kv (adapter :798-905).  layers_per_group > 0 = LMCache's `use_layerwise`
+        (:870-880): the load is issued layer group by layer group and the caller makes the forward
+        pass wait per layer (wait_for_layer_load)."""
         import time
+        self.layer_loads = []
         for m in metas:
             spec = m.load_spec
             if spec is None or not spec.can_load:
@@ -271,6 +276,12 @@ class WorkerState:
                 if m.async_load:
                     ret, ticket = self.engine.retrieve(tokens, mask, sm, stream="detached", return_ticket=True)
                     self.async_loads.append((ticket, m.req_id))
+                elif layers_per_group > 0:
+                    ret, ticket = self.engine.retrieve(tokens, mask, sm, stream=stream, return_ticket=True,
+                                                       layers_per_group=layers_per_group)
+                    if ticket:
+                        self.layer_loads.append((ticket, m.block_ids[masked // self.block_size:
+                                                                   (n + self.block_size - 1) // self.block_size]))
                 else:
                     ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
             except Exception as e:  # no exception on the data path (SURVEY §8b "Errors"): recompute instead
@@ -318,6 +329,17 @@ class WorkerState:
                 self.pending_tickets.append(ticket)
             self.stats.num_stored_tokens += n - lead
             ss.skip_leading_tokens = n
+
+    def wait_layer(self, layer: int, stream=None):
+        for ticket, _blocks in self.layer_loads:
+            self.engine.wait_layer(ticket, layer, stream)
+
+    def abandon_layer_loads(self):
+        """The per-layer hooks did not run in this step (e.g. a full CUDA graph replay): the forward
+        pass may have read pages that were still in flight.  Report them so vLLM recomputes."""
+        for _ticket, blocks in self.layer_loads:
+            self.load_error_blocks.update(blocks)
+        self.layer_loads = []
 
     def reap(self):
         self.pending_tickets = [t for t in self.pending_tickets if not self.engine.poll(t)]

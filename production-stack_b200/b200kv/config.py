@@ -43,6 +43,8 @@ class B200KVConfig:
     variant: int = 0                      # B200KV_VARIANT (0 bulk/TMA, 1 LDG)
     async_load: bool = False              # B200KV_ASYNC_LOAD=1: loads detached from the forward pass (measured
                                           # slower on this workload: +1 scheduler step; profiles/e2e_mrqa_r01.json)
+    layerwise: bool = False               # B200KV_LAYERWISE / LMCACHE_USE_LAYERWISE: per-layer-group loads
+    layer_group: int = 4                  # B200KV_LAYER_GROUP: layers per group
     extra: dict = field(default_factory=dict)
 
     @staticmethod
@@ -81,6 +83,8 @@ class B200KVConfig:
         c.lookup_lease_ms = int(e.get("B200KV_LOOKUP_LEASE_MS", c.lookup_lease_ms))
         c.variant = int(e.get("B200KV_VARIANT", 0))
         c.async_load = _b(e.get("B200KV_ASYNC_LOAD"), False)
+        c.layerwise = _b(e.get("B200KV_LAYERWISE", e.get("LMCACHE_USE_LAYERWISE")), False)
+        c.layer_group = max(1, int(e.get("B200KV_LAYER_GROUP", c.layer_group)))
         for k in _IGNORED:
             if e.get(k) not in (None, "", "0", "False", "false"):
                 logger.warning("%s=%s is accepted for chart compatibility but has no effect in b200kv", k, e.get(k))

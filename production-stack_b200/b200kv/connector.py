@@ -173,6 +173,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                                 staging_bytes=self.cfg.staging_mb << 20, owner=owner_tag_of(self.cfg.instance_id),
                                 variant=self.cfg.variant, key_seed=self._key_seed(rank))
         self._engine.register_kv_caches(tensors)
+        self._layer_index = {name: i for i, name in enumerate(kv_caches.keys())}
+        self._layer_hooks_seen = 0
         self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role)
         try:
             publish_ipc(self._engine_id, self._engine, t0.device.index or 0)   # peers may pull from us
@@ -200,10 +202,23 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         md = self._get_connector_metadata()
         if self._pdw is not None and isinstance(md, B200KVConnectorMetadata) and (md.pd.pulls or md.pd.held):
             self._pdw.start_pulls(md.pd, stream=stream)
-        self._worker.start_load(self._metas(), stream=stream)
+        self._layer_hooks_seen = 0
+        self._worker.start_load(self._metas(), stream=stream,
+                                layers_per_group=self.cfg.layer_group if self.cfg.layerwise else 0)
 
     def wait_for_layer_load(self, layer_name: str) -> None:
-        return  # loads are ordered before the forward pass on the compute stream (stream wait)
+        """Chunk-wise loads are ordered before the forward pass by a stream wait.  Layer-wise loads
+        (B200KV_LAYERWISE=1; LMCache `use_layerwise`, adapter :907-929): the compute stream waits
+        here, once per layer group, while later groups are still crossing PCIe."""
+        w = self._worker
+        if w is None or not w.layer_loads:
+            return
+        idx = self._layer_index.get(layer_name)
+        if idx is None:
+            return
+        self._layer_hooks_seen += 1
+        if idx % self.cfg.layer_group == 0:
+            w.wait_layer(idx, torch.cuda.current_stream())
 
     def save_kv_layer(self, layer_name: str, kv_layer: torch.Tensor, attn_metadata, **kwargs: Any) -> None:
         return  # whole-request store in wait_for_save: CUDA-graph replay skips per-layer hooks (base.py:591-611)
@@ -212,6 +227,14 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
     def wait_for_save(self):
         if self._worker is None:
             return
+        if self._worker.layer_loads and self._layer_hooks_seen == 0:
+            # the per-layer hooks never ran in this step: do not trust the loaded pages, and stop
+            # using the layer-wise path in this process
+            logger.error("b200kv: wait_for_layer_load was not called during a step with layer-wise loads; "
+                         "falling back to chunk-wise loads")
+            self._worker.abandon_layer_loads()
+            self.cfg.layerwise = False
+        self._worker.layer_loads = []
         self._worker.save(self._metas(), stream=torch.cuda.current_stream())
 
     @_traced

@@ -323,7 +323,7 @@ class KVEngine:
         return ticket.value
 
     def retrieve(self, tokens, mask=None, slot_mapping=None, stream=None,
-                 keys: np.ndarray | None = None, return_ticket: bool = False):
+                 keys: np.ndarray | None = None, return_ticket: bool = False, layers_per_group: int = 0):
         """Load every stored chunk after the masked chunk-aligned prefix until the first miss;
         returns the bool mask of tokens that were scheduled to be written (ret_token_mask)."""
         C_ = self.geom.chunk_tokens
@@ -339,9 +339,14 @@ class KVEngine:
             raise ValueError("slot_mapping and tokens differ in length")
         keys = self._keys(tokens) if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
         ticket, loaded = C.c_uint64(0), C.c_int64(0)
-        check(lib().b200kv_load_async(self._h, _ptr(keys, C.c_uint64), len(keys),
-                                       _ptr(sm, C.c_int64), n, skip // C_, _stream_ptr(stream),
-                                       C.byref(ticket), C.byref(loaded)), "b200kv_load_async")
+        if layers_per_group > 0:   # lmcache_engine.retrieve_layer: the caller then waits per layer (wait_layer)
+            check(lib().b200kv_load_layerwise_async(self._h, _ptr(keys, C.c_uint64), len(keys), _ptr(sm, C.c_int64), n,
+                                                     skip // C_, layers_per_group, _stream_ptr(stream),
+                                                     C.byref(ticket), C.byref(loaded)), "b200kv_load_layerwise_async")
+        else:
+            check(lib().b200kv_load_async(self._h, _ptr(keys, C.c_uint64), len(keys),
+                                           _ptr(sm, C.c_int64), n, skip // C_, _stream_ptr(stream),
+                                           C.byref(ticket), C.byref(loaded)), "b200kv_load_async")
         ret[skip:skip + loaded.value] = True
         return (ret, ticket.value) if return_ticket else ret
 
@@ -404,6 +409,10 @@ class KVEngine:
 
     def wait(self, ticket: int):
         check(lib().b200kv_wait(self._h, C.c_uint64(ticket)), "b200kv_wait")
+
+    def wait_layer(self, ticket: int, layer: int, stream=None):
+        """Make `stream` wait until layer `layer` of a layer-wise retrieve is in the pages."""
+        check(lib().b200kv_wait_layer(self._h, C.c_uint64(ticket), layer, _stream_ptr(stream)), "b200kv_wait_layer")
 
     def wait_all(self):
         check(lib().b200kv_wait_all(self._h), "b200kv_wait_all")

@@ -75,7 +75,17 @@ struct Op {
   std::vector<uint64_t> release_keys;  // load: unpin after scatter
   cudaEvent_t done = nullptr;
   std::atomic<int> host_done{0};
+  // layer-wise loads: group_ev[g] fires when layers [g*G, (g+1)*G) of every chunk are in the pages
+  std::vector<cudaEvent_t> group_ev;
+  int layers_per_group = 0;
 };
+
+void destroy_op_events(Op* op) {
+  if (op->done) cudaEventDestroy(op->done);
+  op->done = nullptr;
+  for (cudaEvent_t e : op->group_ev) cudaEventDestroy(e);
+  op->group_ev.clear();
+}
 
 void CUDART_CB op_host_cb(void* p) {
   Op* op = static_cast<Op*>(p);
@@ -396,7 +406,7 @@ PagedSide local_side(const b200kv_ctx* ctx) {
 }
 
 CopyParams make_copy_params(const b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
-                            size_t run_begin, size_t n_runs) {
+                            size_t run_begin, size_t n_runs, uint32_t plane_begin = 0, uint32_t n_planes = 0) {
   CopyParams p{};
   p.paged = local_side(ctx);
   p.peer = p.paged;
@@ -406,7 +416,8 @@ CopyParams make_copy_params(const b200kv_ctx* ctx, const uint8_t* dev_table, con
   p.chunk.token_bytes = ctx->g.fmt_token_bytes;
   p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off) + run_begin;
   p.n_runs = static_cast<uint32_t>(n_runs);
-  p.n_planes = ctx->g.planes;
+  p.n_planes = n_planes ? n_planes : ctx->g.planes;
+  p.plane_begin = plane_begin;
   p.pieces = ctx->pieces;
   p.piece_tokens = ctx->piece_tokens;
   p.total_units = p.n_runs * p.n_planes * p.pieces;
@@ -422,7 +433,8 @@ int launch_hnd_partial(b200kv_ctx* ctx, const CopyParams& cp, const Run* runs, u
   p.chunk = cp.chunk;
   p.runs = runs;
   p.n_runs = n_runs;
-  p.n_planes = ctx->g.planes;
+  p.n_planes = cp.n_planes;
+  p.plane_begin = cp.plane_begin;
   p.n_heads = ctx->g.H;
   p.row_bytes = ctx->g.row_bytes;
   p.total_units = n_runs * p.n_planes * p.n_heads;
@@ -437,8 +449,9 @@ int launch_hnd_partial(b200kv_ctx* ctx, const CopyParams& cp, const Run* runs, u
 // partial-tile runs.  `peer` non-null selects the pull source.
 template <int MODE>
 int launch_copy_runs(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv, size_t run_begin,
-                     size_t n_full, size_t n_partial, cudaStream_t s, const Peer* peer = nullptr) {
-  CopyParams p = make_copy_params(ctx, dev_table, tv, run_begin, n_full);
+                     size_t n_full, size_t n_partial, cudaStream_t s, const Peer* peer = nullptr,
+                     uint32_t plane_begin = 0, uint32_t n_planes = 0) {
+  CopyParams p = make_copy_params(ctx, dev_table, tv, run_begin, n_full, plane_begin, n_planes);
   if (peer) {
     p.peer.bases = peer->d_bases;
     p.peer.block_stride = peer->block_stride;
@@ -484,13 +497,15 @@ int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView&
 }
 
 int launch_fp8_load(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
-                    size_t run_begin, size_t n_runs, cudaStream_t s) {
+                    size_t run_begin, size_t n_runs, cudaStream_t s, uint32_t plane_begin = 0,
+                    uint32_t n_planes = 0) {
   Fp8LoadParams p{};
   p.paged = local_side(ctx);
   p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off) + run_begin;
   p.chunk_addrs = reinterpret_cast<const uint64_t*>(dev_table + tv.addrs_off);
   p.n_runs = static_cast<uint32_t>(n_runs);
-  p.n_planes = ctx->g.planes;
+  p.n_planes = n_planes ? n_planes : ctx->g.planes;
+  p.plane_begin = plane_begin;
   p.chunk_tokens = ctx->g.C;
   p.n_heads = ctx->g.H;
   p.head_bytes = ctx->g.D * 2;
@@ -534,11 +549,39 @@ int copy_chunk(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, cuda
   return B200KV_OK;
 }
 
+// planes [pb, pb+np) of one chunk between the pinned pool and staging (layer-wise loads); the
+// FP8 scales travel once, with the first group.
+int copy_chunk_planes(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, uint32_t pb, uint32_t np,
+                      bool with_scales, cudaMemcpyKind kind, cudaStream_t s) {
+  const Geometry& g = ctx->g;
+  uint8_t* d = static_cast<uint8_t*>(dst) + static_cast<uint64_t>(pb) * g.slab_bytes;
+  const uint8_t* sp = static_cast<const uint8_t*>(src) + static_cast<uint64_t>(pb) * g.slab_bytes;
+  uint64_t moved;
+  if (n_tok == g.C) {
+    moved = static_cast<uint64_t>(np) * g.slab_bytes;
+    CU_TRY(cudaMemcpyAsync(d, sp, moved, kind, s));
+  } else {
+    const uint32_t tok_span = g.hnd ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
+    const size_t width = static_cast<size_t>(tok_span) * g.fmt_token_bytes;
+    CU_TRY(cudaMemcpy2DAsync(d, g.slab_bytes, sp, g.slab_bytes, width, np, kind, s));
+    moved = width * np;
+  }
+  if (with_scales && ctx->cfg.format == B200KV_FMT_FP8) {
+    const size_t sb = static_cast<size_t>(g.planes) * g.H * sizeof(float);
+    CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + g.scales_off, static_cast<const uint8_t*>(src) + g.scales_off,
+                           sb, kind, s));
+    moved += sb;
+  }
+  if (kind == cudaMemcpyDeviceToHost) ctx->stats.d2h_bytes += moved;
+  else ctx->stats.h2d_bytes += moved;
+  return B200KV_OK;
+}
+
 void reap(b200kv_ctx* ctx) {
   for (auto it = ctx->ops.begin(); it != ctx->ops.end();) {
     Op* op = it->second.get();
     if (cudaEventQuery(op->done) == cudaSuccess && op->host_done.load(std::memory_order_acquire)) {
-      cudaEventDestroy(op->done);
+      destroy_op_events(op);
       it = ctx->ops.erase(it);
     } else {
       ++it;
@@ -704,7 +747,7 @@ extern "C" int b200kv_engine_destroy(b200kv_ctx* ctx) {
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     reap(ctx);
-    for (auto& kv : ctx->ops) cudaEventDestroy(kv.second->done);
+    for (auto& kv : ctx->ops) destroy_op_events(kv.second.get());
     ctx->ops.clear();
   }
   if (ctx->pool_registered) cudaHostUnregister(ctx->pool_base);
@@ -938,10 +981,10 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
 // ------------------------------------------------------------------------------------------------
 // load: pinned pool -> staging (DMA) -> paged HBM (kernel), pipelined per chunk
 // ------------------------------------------------------------------------------------------------
-extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
-                                 const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
-                                 void* compute_stream, uint64_t* ticket, int64_t* n_loaded_tokens) {
-  if (!ctx || !keys || !slot_mapping || n_tokens <= 0 || !ticket || skip_chunks < 0)
+static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, const int64_t* slot_mapping,
+                     int64_t n_tokens, int32_t skip_chunks, void* compute_stream, uint64_t* ticket,
+                     int64_t* n_loaded_tokens, int32_t layers_per_group) {
+  if (!ctx || !keys || !slot_mapping || n_tokens <= 0 || !ticket || skip_chunks < 0 || layers_per_group < 0)
     return B200KV_EINVAL;
   if (!ctx->pool || !ctx->kv_registered || ctx->stage.empty()) return B200KV_EINVAL;
   const Geometry& g = ctx->g;
@@ -994,7 +1037,81 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
   timing_reset(ctx, 1);
   const size_t n_stage = ctx->stage.size() - ctx->n_store_slots;
   int64_t loaded = 0;
-  for (size_t b0 = 0; b0 < todo.size(); b0 += n_stage) {
+  // Layer-wise: every chunk must own a staging slot for the whole op (the groups of all chunks are
+  // interleaved); an op larger than the load half of the ring falls back to the chunk-wise path.
+  const bool layerwise = layers_per_group > 0 && todo.size() <= n_stage;
+  if (layerwise) {
+    const uint32_t G = static_cast<uint32_t>(layers_per_group);
+    const uint32_t n_groups = (g.L + G - 1) / G;
+    const size_t nb = todo.size();
+    std::vector<Run> runs;
+    std::vector<uint32_t> offs(nb + 1), n_full_of(nb), sidx(nb);
+    std::vector<uint64_t> addrs(nb);
+    for (size_t i = 0; i < nb; ++i) {
+      const Todo& t = todo[i];
+      offs[i] = static_cast<uint32_t>(runs.size());
+      const int64_t tb = static_cast<int64_t>(t.c) * g.C;
+      std::vector<Run> cf, cp;
+      int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf,
+                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &cp);
+      if (rc) return rc;
+      n_full_of[i] = static_cast<uint32_t>(cf.size());
+      runs.insert(runs.end(), cf.begin(), cf.end());
+      runs.insert(runs.end(), cp.begin(), cp.end());
+      sidx[i] = ctx->n_store_slots + ctx->load_next;
+      ctx->load_next = (ctx->load_next + 1) % static_cast<uint32_t>(n_stage);
+      addrs[i] = reinterpret_cast<uint64_t>(ctx->d_staging) + static_cast<uint64_t>(sidx[i]) * g.chunk_bytes;
+      StageSlot& ss = ctx->stage[sidx[i]];
+      if (ss.used) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, ss.free_ev, 0));
+      loaded += t.n_tok;
+    }
+    offs[nb] = static_cast<uint32_t>(runs.size());
+    TableView tv;
+    int rc = table_acquire(ctx, runs.size(), nb, &tv);
+    if (rc) return rc;
+    std::memcpy(tv.slot->host + tv.runs_off, runs.data(), runs.size() * sizeof(Run));
+    std::memcpy(tv.slot->host + tv.addrs_off, addrs.data(), nb * 8);
+    std::memcpy(tv.slot->host + tv.offs_off, offs.data(), (nb + 1) * 4);
+    rc = table_upload(ctx, tv, ctx->s_scatter);
+    if (rc) return rc;
+    op->layers_per_group = layers_per_group;
+    op->group_ev.resize(n_groups, nullptr);
+    cudaEvent_t landed;
+    CU_TRY(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+    for (uint32_t gi = 0; gi < n_groups; ++gi) {
+      const uint32_t pb = 2 * gi * G;
+      const uint32_t np = std::min<uint32_t>(2 * G, g.planes - pb);
+      for (size_t i = 0; i < nb; ++i) {
+        rc = copy_chunk_planes(ctx, reinterpret_cast<void*>(addrs[i]), b200kv_pool_slot_ptr(ctx->pool, todo[i].slot),
+                               todo[i].n_tok, pb, np, gi == 0, cudaMemcpyHostToDevice, ctx->s_h2d);
+        if (rc) return rc;
+      }
+      CU_TRY(cudaEventRecord(landed, ctx->s_h2d));           // this group of every chunk has landed
+      CU_TRY(cudaStreamWaitEvent(ctx->s_scatter, landed, 0));
+      rc = timing_begin(ctx, 1, ctx->s_scatter);
+      if (rc) return rc;
+      if (ctx->cfg.format == B200KV_FMT_FP8) {
+        rc = launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), ctx->s_scatter, pb, np);
+      } else {
+        // one launch per chunk keeps the (full, partial) run split of each chunk
+        for (size_t i = 0; i < nb && rc == B200KV_OK; ++i)
+          rc = launch_copy_runs<kLoad>(ctx, tv.slot->dev, tv, offs[i], n_full_of[i],
+                                       offs[i + 1] - offs[i] - n_full_of[i], ctx->s_scatter, nullptr, pb, np);
+      }
+      if (rc) return rc;
+      rc = timing_end(ctx, 1, ctx->s_scatter);
+      if (rc) return rc;
+      CU_TRY(cudaEventCreateWithFlags(&op->group_ev[gi], cudaEventDisableTiming));
+      CU_TRY(cudaEventRecord(op->group_ev[gi], ctx->s_scatter));
+    }
+    CU_TRY(cudaEventDestroy(landed));
+    for (size_t i = 0; i < nb; ++i) {
+      CU_TRY(cudaEventRecord(ctx->stage[sidx[i]].free_ev, ctx->s_scatter));
+      ctx->stage[sidx[i]].used = true;
+    }
+    CU_TRY(cudaEventRecord(tv.slot->done_ev, ctx->s_scatter));
+  }
+  for (size_t b0 = 0; !layerwise && b0 < todo.size(); b0 += n_stage) {
     const size_t nb = std::min(n_stage, todo.size() - b0);
     std::vector<Run> runs;
     std::vector<uint32_t> offs(nb + 1);
@@ -1054,11 +1171,46 @@ extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t 
   }
   CU_TRY(cudaLaunchHostFunc(ctx->s_scatter, op_host_cb, op.get()));
   CU_TRY(cudaEventRecord(op->done, ctx->s_scatter));
-  if (!detached) CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));  // the forward pass must see the loaded pages
+  // chunk-wise: the forward pass must see the loaded pages; layer-wise: it waits per layer instead
+  if (!detached && !layerwise) CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));
   ctx->stats.n_loaded_tokens += loaded;
   if (n_loaded_tokens) *n_loaded_tokens = loaded;
   *ticket = op->id;
   ctx->ops.emplace(op->id, std::move(op));
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
+                                 const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
+                                 void* compute_stream, uint64_t* ticket, int64_t* n_loaded_tokens) {
+  return load_impl(ctx, keys, n_chunks, slot_mapping, n_tokens, skip_chunks, compute_stream, ticket,
+                   n_loaded_tokens, 0);
+}
+
+extern "C" int b200kv_load_layerwise_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
+                                           const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
+                                           int32_t layers_per_group, void* compute_stream, uint64_t* ticket,
+                                           int64_t* n_loaded_tokens) {
+  if (layers_per_group <= 0) return B200KV_EINVAL;
+  return load_impl(ctx, keys, n_chunks, slot_mapping, n_tokens, skip_chunks, compute_stream, ticket,
+                   n_loaded_tokens, layers_per_group);
+}
+
+extern "C" int b200kv_wait_layer(b200kv_ctx* ctx, uint64_t ticket, int32_t layer, void* compute_stream) {
+  if (!ctx || layer < 0) return B200KV_EINVAL;
+  if (ticket == 0) return B200KV_OK;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->ops.find(ticket);
+  if (it == ctx->ops.end()) return B200KV_OK;  // finished and reaped: the pages are already there
+  Op* op = it->second.get();
+  cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
+  if (op->group_ev.empty()) {  // the op fell back to the chunk-wise path: wait for all of it
+    CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));
+    return B200KV_OK;
+  }
+  const size_t gi = std::min<size_t>(static_cast<size_t>(layer / op->layers_per_group), op->group_ev.size() - 1);
+  CU_TRY(cudaStreamWaitEvent(cs, op->group_ev[gi], 0));
   return B200KV_OK;
 }
 
@@ -1075,7 +1227,7 @@ extern "C" int b200kv_poll(b200kv_ctx* ctx, uint64_t ticket, int* done) {
   Op* op = it->second.get();
   const cudaError_t q = cudaEventQuery(op->done);
   if (q == cudaSuccess && op->host_done.load(std::memory_order_acquire)) {
-    cudaEventDestroy(op->done);
+    destroy_op_events(op);
     ctx->ops.erase(it);
     *done = 1;
   } else if (q == cudaSuccess || q == cudaErrorNotReady) {
@@ -1103,7 +1255,7 @@ extern "C" int b200kv_wait(b200kv_ctx* ctx, uint64_t ticket) {
   auto it = ctx->ops.find(ticket);
   if (it != ctx->ops.end()) {
     while (!it->second->host_done.load(std::memory_order_acquire)) { /* callback precedes event */ }
-    cudaEventDestroy(it->second->done);
+    destroy_op_events(it->second.get());
     ctx->ops.erase(it);
   }
   return B200KV_OK;

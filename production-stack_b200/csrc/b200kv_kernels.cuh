@@ -60,7 +60,8 @@ struct CopyParams {
   ChunkSide chunk;
   const Run* runs;
   uint32_t n_runs;
-  uint32_t n_planes;      // 2*L
+  uint32_t n_planes;      // planes covered by this launch (2*L, or one layer group of it)
+  uint32_t plane_begin;   // first plane of the launch (layer-wise loads walk the planes in groups)
   uint32_t pieces;        // pieces per run = ceil(block_tokens / piece_tokens)
   uint32_t piece_tokens;  // tokens per piece (piece bytes <= stage bytes)
   uint32_t total_units;   // n_runs * n_planes * pieces
@@ -197,7 +198,7 @@ struct Unit {
 template <int MODE>
 __device__ __forceinline__ Unit decode_unit(const CopyParams& p, uint32_t u) {
   // plane fastest: consecutive units of one CTA stride across planes of the same run.
-  const uint32_t plane = u % p.n_planes;
+  const uint32_t plane = p.plane_begin + u % p.n_planes;
   const uint32_t t = u / p.n_planes;
   const uint32_t piece = t % p.pieces;
   const uint32_t r = t / p.pieces;
@@ -303,6 +304,7 @@ struct HndParams {
   ChunkSide chunk;       // chunk.token_bytes = H*D*elem; a tile = block_tokens * token_bytes
   const Run* runs;
   uint32_t n_runs, n_planes, n_heads;
+  uint32_t plane_begin;
   uint32_t row_bytes;    // D * elem: one (token, head) row
   uint32_t total_units;  // n_runs * n_planes * n_heads
 };
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(128) kv_hnd_partial_kernel(const HndParams p) 
   for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x) {
     const uint32_t h = ui % p.n_heads;
     const uint32_t t = ui / p.n_heads;
-    const uint32_t plane = t % p.n_planes;
+    const uint32_t plane = p.plane_begin + t % p.n_planes;
     const Run run = p.runs[t / p.n_planes];
     uint64_t src, dst;
     if (MODE == kStore) {
@@ -572,6 +574,7 @@ struct Fp8LoadParams {
   uint64_t scales_off;
   uint32_t total_units;
   uint32_t hnd;
+  uint32_t plane_begin;
 };
 
 __device__ __forceinline__ uint4 dequant8(const uint2& q, float scale) {
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(kFp8Threads) kv_fp8_load_kernel(const Fp8LoadP
 
   uint32_t phase = 0;
   for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x, phase ^= 1u) {
-    const uint32_t plane = ui % p.n_planes;
+    const uint32_t plane = p.plane_begin + ui % p.n_planes;
     const Run run = p.runs[ui / p.n_planes];
     const uint32_t c = static_cast<uint32_t>(run.b) / p.chunk_tokens;
     const uint32_t t = static_cast<uint32_t>(run.b) - c * p.chunk_tokens;

@@ -517,3 +517,47 @@ def test_hnd_peer_pull_and_format_isolation():
     e_n.close()
     e_h.close()
     pool.close()
+
+
+@pytest.mark.parametrize("layout", ["nhd", "hnd"])
+@pytest.mark.parametrize("fmt", [FMT_RAW, FMT_FP8])
+@pytest.mark.parametrize("group", [1, 2, 5])
+def test_layerwise_retrieve_matches_oracle(group, fmt, layout):
+    """lmcache_engine.retrieve_layer semantics (adapter :870-880, :907-929): same pages as the
+    chunk-wise retrieve; a stream that waited for layer l sees layers <= l complete."""
+    need_gpu()
+    L, NB, bs, H, D, C_ = 5, 96, 16, 8, 128, 256
+    rng = np.random.default_rng(900 + group)
+    host = mk_host_layers(rng, L, NB, bs, H, D)
+    hnd = layout == "hnd"
+    dev = to_dev_hnd(host) if hnd else to_dev(host)
+    geom = KVGeometry(L, H, D, NB, bs, C_, 2, 2 * bs * H * D * 2 if hnd else 0, fmt,
+                      b200kv._lib.LAYOUT_HND if hnd else b200kv._lib.LAYOUT_NHD)
+    pool = KVPool(None, 8 * geom.chunk_bytes, geom.chunk_bytes, 1)
+    eng = KVEngine(geom, pool, 0, staging_bytes=8 * geom.chunk_bytes)
+    eng.register_kv_caches(dev)
+    n = 2 * C_ + 70
+    toks = rng.integers(0, 1000, n).astype(np.int32)
+    sm = ko.slot_mapping_from_blocks(rng.permutation(NB)[: (n + 15) // 16], 16, n)
+    dm = ko.slot_mapping_from_blocks(rng.permutation(NB)[: (n + 15) // 16], 16, n)
+    eng.wait(eng.store(toks, None, sm))
+    for t in dev:
+        t.zero_()
+    side = torch.cuda.Stream()
+    ret, ticket = eng.retrieve(toks, None, dm, stream=torch.cuda.current_stream(), return_ticket=True,
+                               layers_per_group=group)
+    assert ret.all() and ticket
+    want = [np.zeros_like(l) for l in host]
+    oe = ko.OracleEngine(C_, "fp8" if fmt == FMT_FP8 else "raw")
+    oe.store(toks, np.ones(n, bool), host, sm)
+    oe.retrieve(toks, np.ones(n, bool), want, dm)
+    get = (lambda t: logical_bits(t)) if hnd else bits_of
+    for l in range(L):
+        eng.wait_layer(ticket, l, side)          # what wait_for_layer_load does on the compute stream
+        side.synchronize()
+        assert np.array_equal(get(dev[l]), want[l]), f"layer {l} not complete after its wait"
+    eng.wait(ticket)
+    eng.wait_layer(ticket, 0, side)              # finished tickets: no-op
+    assert eng.stats()["n_loaded_tokens"] == n
+    eng.close()
+    pool.close()
