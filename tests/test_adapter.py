@@ -25,7 +25,10 @@ class OracleBackedEngine:
         self.oe.store(tokens, mask, self.layers, slot_mapping, offset)
         return 1
 
-    def retrieve(self, tokens, mask, slot_mapping, stream=None, return_ticket=False):
+    def retrieve(self, tokens, mask, slot_mapping, stream=None, return_ticket=False, layers_per_group=0):
+        if layers_per_group:
+            self.calls.append(("retrieve_layerwise", len(tokens), layers_per_group))
+            return self.oe.retrieve(tokens, mask, self.layers, slot_mapping), 91
         self.calls.append(("retrieve", len(tokens), int((~mask).sum()), stream))
         ret = self.oe.retrieve(tokens, mask, self.layers, slot_mapping)
         return (ret, 77) if return_ticket else ret
@@ -34,6 +37,9 @@ class OracleBackedEngine:
 
     def poll(self, t):
         return self.done
+
+    def wait_layer(self, ticket, layer, stream=None):
+        self.calls.append(("wait_layer", ticket, layer))
 
 
 def sched_out(new=(), cached=None, num_sched=None, finished=()):
@@ -233,3 +239,25 @@ def test_engine_failures_never_raise_on_the_data_path():
     a = ReqMeta("y", np.arange(C, dtype=np.int32), [1, 2, 3, 4], load_spec=LoadSpec(0, C, True), async_load=True)
     w.start_load([a])
     assert w.poll_async_loads() == {"y"} and w.take_load_errors() == {1, 2, 3, 4}
+
+
+def test_layerwise_worker_flow_and_safety_net():
+    """LMCache `use_layerwise`: start_load issues a layer-wise retrieve, wait_for_layer_load forwards
+    per layer; if the hooks never ran the loaded blocks are reported for recompute."""
+    rng = np.random.default_rng(8)
+    layers = [rng.integers(0, 2 ** 16, (2, 64, BS, 2, 8), dtype=np.uint16) for _ in range(2)]
+    eng = OracleBackedEngine(layers)
+    w = WorkerState(eng, BS, C)
+    toks = np.arange(2 * C, dtype=np.int32)
+    sm = ko.slot_mapping_from_blocks(list(range(8)), BS, 2 * C)
+    eng.oe.store(toks, np.ones(2 * C, bool), layers, sm)
+    m = ReqMeta("r", toks, list(range(20, 28)), load_spec=LoadSpec(C, 2 * C, True))
+    w.start_load([m], layers_per_group=4)
+    assert eng.calls[-1] == ("retrieve_layerwise", 2 * C, 4)
+    assert w.layer_loads == [(91, list(range(24, 28)))]        # the blocks past vLLM's own prefix hit
+    w.wait_layer(4)
+    assert eng.calls[-1] == ("wait_layer", 91, 4)
+    w.abandon_layer_loads()
+    assert w.take_load_errors() == {24, 25, 26, 27} and w.layer_loads == []
+    w.start_load([])                                            # a new step forgets the previous tickets
+    assert w.layer_loads == []
