@@ -203,8 +203,11 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         if self._pdw is not None and isinstance(md, B200KVConnectorMetadata) and (md.pd.pulls or md.pd.held):
             self._pdw.start_pulls(md.pd, stream=stream)
         self._layer_hooks_seen = 0
+        # A step replayed as ONE full CUDA graph never runs the per-layer hooks (base.py:591-611): use
+        # the chunk-wise load there (e.g. a full-prompt hit that only recomputes its last token).
+        full_graph = getattr(getattr(forward_context, "cudagraph_runtime_mode", None), "name", "NONE") == "FULL"
         self._worker.start_load(self._metas(), stream=stream,
-                                layers_per_group=self.cfg.layer_group if self.cfg.layerwise else 0)
+                                layers_per_group=self.cfg.layer_group if (self.cfg.layerwise and not full_graph) else 0)
 
     def wait_for_layer_load(self, layer_name: str) -> None:
         """Chunk-wise loads are ordered before the forward pass by a stream wait.  Layer-wise loads

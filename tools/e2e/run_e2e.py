@@ -6,7 +6,7 @@ Modes:
   none      no connector, prefix caching off   -> every turn re-prefills its whole context
   b200kv    this repo's connector, RAW (bit-exact) format
   b200kv8   this repo's connector, FP8 packed format
-  b200kv_lw / b200kv8_lw      layer-wise loads (PCIe transfer overlapped with the forward pass)
+  b200kv_cw / b200kv8_cw      chunk-wise loads (layer-wise overlap with the forward pass switched off)
   b200kv_async / b200kv_c64  variants: loads detached from the forward step / 64-token chunks
   offload   vLLM's in-tree CPU offload connector (same plugin slot; the runnable same-box stand-in
             for the absent lmcache wheel, SURVEY.md §8d "baseline 2a")
@@ -41,7 +41,7 @@ def connector_args(mode: str, cpu_gb: float):
                    LMCACHE_CHUNK_SIZE="64" if "c64" in mode else "256",
                    B200KV_FORMAT="fp8" if "8" in mode.replace("c64", "") else "raw",
                    B200KV_ASYNC_LOAD="1" if "async" in mode else "0",
-                   B200KV_LAYERWISE="1" if "lw" in mode else "0")
+                   B200KV_LAYERWISE="0" if "cw" in mode else "1")
         cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}
         return ["--kv-transfer-config", json.dumps(cfg)], env
     if mode == "offload":
