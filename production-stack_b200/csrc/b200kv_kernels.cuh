@@ -464,23 +464,29 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
   mbar_wait(&bar, 0);
 
   const uint32_t vpt = tb >> 4;  // 16-byte vectors per token
-  // HND window = W/bs whole tiles [H][bs][D]: vector idx = ((tile*H + h)*bs + row)*rv + c.  With 256
-  // threads and bs*rv == 256 all lanes of a warp share (tile, h) in one iteration.
+  // HND window = W/bs whole tiles [H][bs][D]: vector idx = ((tile*H + h)*bs + row)*rv + c.
   const uint32_t rv = p.head_bytes >> 4;                 // 16-byte vectors per (token, head) row
   const uint32_t tile_rows = p.paged.block_tokens * rv;  // vectors per (tile, head)
-  const uint32_t hnd_total = (W / p.paged.block_tokens) * p.n_heads * tile_rows;
+  const uint32_t n_tiles = W / p.paged.block_tokens;
   if (p.hnd) {
-    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kThreads) {
-      const uint32_t rowi = (idx / rv) % p.paged.block_tokens;
-      const uint32_t h = (idx / tile_rows) % p.n_heads;
-      const uint32_t tile = idx / (tile_rows * p.n_heads);
-      uint32_t m = 0;
-      if (tile * p.paged.block_tokens + rowi < n_valid) {
-        const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(idx) * 16);
-        const uint32_t acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(0u, v.x), v.y), v.z), v.w);
-        m = max(acc & 0xffffu, acc >> 16);
+    // One warp per head (heads w, w+8, ...): the valid rows of a (tile, head) block are a prefix of it
+    // ([bs][D] rows are contiguous), so the warp streams the block with 16-byte loads, folds the lanes
+    // with one REDUX and owns s_absmax[h] — no index arithmetic per vector, no atomics.
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t h = threadIdx.x >> 5; h < p.n_heads; h += kThreads >> 5) {
+      uint32_t acc = 0;
+      for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        const uint32_t t0 = tile * p.paged.block_tokens;
+        const uint32_t nv = (n_valid > t0 ? min(p.paged.block_tokens, n_valid - t0) : 0u) * rv;
+        const uint8_t* blk = smem + static_cast<size_t>(tile * p.n_heads + h) * tile_rows * 16;
+#pragma unroll 8
+        for (uint32_t v = lane; v < nv; v += 32) {
+          const uint4 x = *reinterpret_cast<const uint4*>(blk + static_cast<size_t>(v) * 16);
+          acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(acc, x.x), x.y), x.z), x.w);
+        }
       }
-      if (m) atomicMax(&s_absmax[h], m);
+      const uint32_t m = __reduce_max_sync(0xffffffffu, max(acc & 0xffffu, acc >> 16));
+      if (lane == 0) s_absmax[h] = m;
     }
   } else {
   // ---- per-head absmax over this CTA's tokens: a thread's 16-byte column has a fixed head ----
@@ -529,13 +535,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     // the packed slab mirrors the tiles at half size: same vector index, 8 bytes each
     uint8_t* outh = reinterpret_cast<uint8_t*>(p.chunk_addrs[c] + static_cast<uint64_t>(plane) * p.slab_q_bytes +
                                                static_cast<uint64_t>(rank * W) * (tb >> 1));
-    for (uint32_t idx = threadIdx.x; idx < hnd_total; idx += kThreads) {
-      const uint32_t rowi = (idx / rv) % p.paged.block_tokens;
-      const uint32_t h = (idx / tile_rows) % p.n_heads;
-      const uint32_t tile = idx / (tile_rows * p.n_heads);
-      if (tile * p.paged.block_tokens + rowi >= n_valid) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(smem + static_cast<size_t>(idx) * 16);
-      st_na_v2(outh + static_cast<size_t>(idx) * 8, quant8(v, s_inv[h]));
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t h = threadIdx.x >> 5; h < p.n_heads; h += kThreads >> 5) {
+      const float inv = s_inv[h];
+      for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        const uint32_t t0 = tile * p.paged.block_tokens;
+        const uint32_t nv = (n_valid > t0 ? min(p.paged.block_tokens, n_valid - t0) : 0u) * rv;
+        const size_t base = static_cast<size_t>(tile * p.n_heads + h) * tile_rows;
+#pragma unroll 8
+        for (uint32_t v = lane; v < nv; v += 32) {
+          const uint4 x = *reinterpret_cast<const uint4*>(smem + (base + v) * 16);
+          st_na_v2(outh + (base + v) * 8, quant8(x, inv));
+        }
+      }
     }
     return;
   }

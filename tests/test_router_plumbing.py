@@ -23,6 +23,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SRC = "/root/reference/src"
+if not os.path.isdir(os.path.join(REF_SRC, "vllm_router")):
+    REF_SRC = os.path.join(ROOT, "baseline", "_ref")   # offline pip install of the same, unmodified (build())
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_SRC, "vllm_router")),
                                 reason="reference router not present on this machine")
 
