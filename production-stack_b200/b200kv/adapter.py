@@ -234,6 +234,7 @@ class WorkerStats:
     num_stored_tokens: int = 0
     num_loaded_tokens: int = 0
     num_load_shortfalls: int = 0
+    num_foreign_loaded_tokens: int = 0   # loaded from chunks another replica stored (shared pool)
     retrieve_seconds: float = 0.0
     retrieve_calls: int = 0
 
@@ -241,8 +242,9 @@ class WorkerStats:
 class WorkerState:
     """Worker-role half: turns ReqMeta into engine.store / engine.retrieve calls."""
 
-    def __init__(self, engine, block_size: int, chunk: int, kv_role: str = "kv_both"):
+    def __init__(self, engine, block_size: int, chunk: int, kv_role: str = "kv_both", owner_tag: int = 0):
         self.engine = engine
+        self.owner_tag = owner_tag   # != 0: count tokens served from chunks stored under another owner tag
         self.block_size = block_size
         self.chunk = chunk
         self.kv_role = kv_role
@@ -293,6 +295,8 @@ class WorkerState:
             self.stats.retrieve_calls += 1
             got = int(ret.sum())
             self.stats.num_loaded_tokens += got
+            if got and self.owner_tag:
+                self.stats.num_foreign_loaded_tokens += self._foreign_tokens(tokens, masked, masked + got)
             if masked + got < n:
                 # short load: report the blocks vLLM believes are filled so it recomputes them
                 # (KVConnectorBase_V1.get_block_ids_with_load_errors, base.py:375-393)
@@ -300,6 +304,19 @@ class WorkerState:
                 first_bad = (masked + got) // self.block_size
                 last = (n + self.block_size - 1) // self.block_size
                 self.load_error_blocks.update(m.block_ids[first_bad:last])
+
+    def _foreign_tokens(self, tokens, lo: int, hi: int) -> int:
+        """Tokens of [lo, hi) that sit in chunks first stored by ANOTHER instance of a shared pool
+        (BASELINE.json config 3): what cross-replica reuse actually served."""
+        try:
+            n_hit, owners = self.engine.pool.lookup_owner(self.engine._keys(tokens[:hi]))
+        except Exception:
+            return 0
+        out = 0
+        for c in range(lo // self.chunk, min(n_hit, (hi + self.chunk - 1) // self.chunk)):
+            if int(owners[c]) != self.owner_tag:
+                out += min(hi, (c + 1) * self.chunk) - max(lo, c * self.chunk)
+        return out
 
     def save(self, metas: list[ReqMeta], stream=None):
         """wait_for_save (adapter :1033-1128).  Blocks only until the gather kernels are queued;

@@ -175,7 +175,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._engine.register_kv_caches(tensors)
         self._layer_index = {name: i for i, name in enumerate(kv_caches.keys())}
         self._layer_hooks_seen = 0
-        self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role)
+        self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role,
+                                   owner_tag=owner_tag_of(self.cfg.instance_id) if self.cfg.pool_name else 0)
         try:
             publish_ipc(self._engine_id, self._engine, t0.device.index or 0)   # peers may pull from us
             self._pdw = PDWorker(self._engine, self._engine_id, self._block_size)
@@ -269,7 +270,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         ps = self._pool.stats()
         cur = {"num_stored_tokens": ws.num_stored_tokens, "num_loaded_tokens": ws.num_loaded_tokens,
                "retrieve_seconds": ws.retrieve_seconds, "retrieve_calls": ws.retrieve_calls,
-               "load_shortfalls": ws.num_load_shortfalls,
+               "load_shortfalls": ws.num_load_shortfalls, "num_foreign_loaded_tokens": ws.num_foreign_loaded_tokens,
                "num_hit_tokens": ps["n_hit_tokens"], "num_requested_tokens": ps["n_requested_tokens"],
                "retrieve_bytes": ws.num_loaded_tokens * self._engine.geom.payload_bytes_per_token,
                "store_bytes": ws.num_stored_tokens * self._engine.geom.payload_bytes_per_token}

@@ -14,7 +14,8 @@ from typing import Any
 from vllm.distributed.kv_transfer.kv_connector.v1.metrics import KVConnectorPromMetrics, KVConnectorStats
 
 _SUM_KEYS = ("num_hit_tokens", "num_requested_tokens", "num_stored_tokens", "num_loaded_tokens",
-             "retrieve_seconds", "retrieve_calls", "retrieve_bytes", "store_bytes", "load_shortfalls")
+             "retrieve_seconds", "retrieve_calls", "retrieve_bytes", "store_bytes", "load_shortfalls",
+             "num_foreign_loaded_tokens")
 
 
 @dataclass
@@ -36,7 +37,7 @@ class B200KVStats(KVConnectorStats):
     def reduce(self) -> dict[str, int | float]:
         d = self.data
         out: dict[str, int | float] = {k: d[k] for k in ("num_hit_tokens", "num_requested_tokens", "num_stored_tokens",
-                                                          "num_loaded_tokens") if k in d}
+                                                          "num_loaded_tokens", "num_foreign_loaded_tokens") if k in d}
         if d.get("retrieve_seconds"):
             out["retrieve_GBps"] = round(d.get("retrieve_bytes", 0) / d["retrieve_seconds"] / 1e9, 2)
         if "local_cache_usage_bytes" in d:
@@ -61,6 +62,9 @@ class B200KVPromMetrics(KVConnectorPromMetrics):
                                 labelnames=labelnames))
         self.stored = per_engine(c(name="lmcache:num_stored_tokens", documentation="tokens stored to the KV pool",
                                    labelnames=labelnames))
+        self.foreign = per_engine(c(name="b200kv:cross_replica_loaded_tokens",
+                                    documentation="tokens loaded from chunks another replica stored (shared pool)",
+                                    labelnames=labelnames))
         self.usage = per_engine(g(name="lmcache:local_cache_usage", documentation="bytes of pinned host pool in use",
                                   labelnames=labelnames, multiprocess_mode="mostrecent"))
         self.r_sum = per_engine(c(name="lmcache:retrieve_speed_sum", documentation="sum of retrieve speeds (tokens/s)",
@@ -73,6 +77,7 @@ class B200KVPromMetrics(KVConnectorPromMetrics):
         self.hit[engine_idx].inc(d.get("num_hit_tokens", 0))
         self.req[engine_idx].inc(d.get("num_requested_tokens", 0))
         self.stored[engine_idx].inc(d.get("num_stored_tokens", 0))
+        self.foreign[engine_idx].inc(d.get("num_foreign_loaded_tokens", 0))
         if "local_cache_usage_bytes" in d:
             self.usage[engine_idx].set(d["local_cache_usage_bytes"])
         if d.get("retrieve_calls") and d.get("retrieve_seconds"):

@@ -261,3 +261,23 @@ def test_layerwise_worker_flow_and_safety_net():
     assert w.take_load_errors() == {24, 25, 26, 27} and w.layer_loads == []
     w.start_load([])                                            # a new step forgets the previous tickets
     assert w.layer_loads == []
+
+
+def test_foreign_tokens_counts_chunks_of_other_owners(shm_name):
+    """Shared pool (BASELINE.json config 3): tokens served from chunks another replica stored."""
+    from b200kv.engine import KVPool, chunk_keys
+
+    pool = KVPool(shm_name, 64 * 1024, 1024, 3)
+    toks = np.arange(3 * C + 10, dtype=np.int32)
+    keys = chunk_keys(toks, C, 7, True)
+    for i, (k, owner) in enumerate(zip(keys, (11, 22, 22, 11))):
+        pool.reserve(int(k), min(C, len(toks) - i * C), 0, owner)
+        pool.commit(int(k))
+    eng = NS(pool=pool, _keys=lambda t: chunk_keys(t, C, 7, True))
+    w = WorkerState(eng, BS, C, owner_tag=11)
+    assert w._foreign_tokens(toks, 0, len(toks)) == 2 * C            # chunks 1 and 2 belong to owner 22
+    assert w._foreign_tokens(toks, C + 8, 3 * C) == 2 * C - 8        # clipped to the loaded range
+    assert w._foreign_tokens(toks, 0, C) == 0
+    assert WorkerState(eng, BS, C, owner_tag=22)._foreign_tokens(toks, 0, len(toks)) == C + 10
+    pool.close()
+    KVPool.unlink(shm_name)

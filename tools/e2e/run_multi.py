@@ -96,6 +96,10 @@ def main():
                  ("--user-history-prompt", 1536), ("--answer-len", 64)):
         ap.add_argument(a, type=int, default=d)
     ap.add_argument("--qps", type=float, default=4.0)
+    ap.add_argument("--same-gpu", action="store_true",
+                    help="all replicas on GPU 0 (functional check of cross-replica reuse on one GPU: started one "
+                         "after the other, --gpu-mem-util split between them; timings are not per-replica numbers)")
+    ap.add_argument("--extra", default="", help="extra vllm serve args, e.g. --extra=--enforce-eager")
     ap.add_argument("--mock", action="store_true", help="orchestration dry run: tools/mock_backend.py instead of vllm (no GPU)")
     args = ap.parse_args()
     os.makedirs(args.log_dir, exist_ok=True)
@@ -106,23 +110,29 @@ def main():
     results = []
     for mode in args.modes.split(","):
         procs, logs = [], []
-        res = {"mode": mode, "replicas": args.replicas, "routing": args.routing, "router": rpath}
+        t_mode = time.time()
+        res = {"mode": mode, "same_gpu": args.same_gpu, "replicas": args.replicas, "routing": args.routing, "router": rpath}
         try:
             ports = [8100 + i for i in range(args.replicas)]
             for i, port in enumerate(ports):
                 gb = args.cpu_gb * (args.replicas if mode.startswith("shared") else 1)
-                env, cargs = replica_env(mode, i, gb, f"{os.getpid()}-{mode}")
+                env, cargs = replica_env(mode, 0 if args.same_gpu else i, gb, f"{os.getpid()}-{mode}")
+                env["LMCACHE_LMCACHE_INSTANCE_ID"] = f"replica-{i}"
+                util = args.gpu_mem_util / args.replicas if args.same_gpu else args.gpu_mem_util
                 cmd = [sys.executable, "-m", "vllm.entrypoints.openai.api_server", "--model", args.model_dir,
                        "--served-model-name", MODEL, "--load-format", "dummy", "--dtype", "bfloat16",
                        "--max-model-len", str(args.max_model_len), "--no-enable-prefix-caching",
-                       "--gpu-memory-utilization", str(args.gpu_mem_util), "--port", str(port), "--seed", "0",
-                       "--host", "127.0.0.1"] + cargs
+                       "--gpu-memory-utilization", str(util), "--port", str(port), "--seed", "0",
+                       "--host", "127.0.0.1"] + cargs + (args.extra.split() if args.extra else [])
                 if args.mock:
                     cmd = [sys.executable, os.path.join(ROOT, "tools", "mock_backend.py"), "--port", str(port), "--model", MODEL]
                 log = open(os.path.join(args.log_dir, f"vllm_{mode}_{i}.log"), "w")
                 logs.append(log)
                 procs.append(subprocess.Popen(cmd, env=env, stdout=log, stderr=subprocess.STDOUT, start_new_session=True))
-            if not all(wait_ready(p, pr, args.startup_timeout) for p, pr in zip(ports, procs)):
+                if args.same_gpu and not wait_ready(port, procs[-1], args.startup_timeout):
+                    break
+            res["startup_s"] = time.time() - t_mode
+            if len(procs) != len(ports) or not all(wait_ready(p, pr, args.startup_timeout) for p, pr in zip(ports, procs)):
                 res["error"] = "replicas not ready"
                 continue
             renv = dict(os.environ)
