@@ -47,6 +47,7 @@ extern "C" {
 #define B200KV_ENOSPC (-28)   /* pool full and nothing evictable                            */
 #define B200KV_ENOTSUP (-95)  /* layout / feature not supported by this build               */
 #define B200KV_EBUSY (-16)    /* resource still in use                                      */
+#define B200KV_EIO (-5)       /* remote tier: connection lost / short read or write         */
 
 /* ---- formats of a stored chunk -------------------------------------------------------- */
 /* RAW  : (L, 2, C, H, D) elements of the cache dtype, token-major — the LMCache `kv_shape`
@@ -282,6 +283,40 @@ int b200kv_engine_get_stats(b200kv_ctx* ctx, b200kv_engine_stats* out);
  * events on the launching stream (valid after the op's ticket completed or the stream was
  * synchronised).  which: 0 = gather, 1 = scatter, 2 = peer pull.                           */
 int b200kv_last_kernel_ms(b200kv_ctx* ctx, int which, float* ms_out);
+
+/* ======================================================================================= */
+/* remote group (CPU only): the cache-server tier                                           */
+/* ======================================================================================= */
+/* Stand-in for LMCache's cache server and its client: the chart runs
+ * `/opt/venv/bin/lmcache_server 0.0.0.0 <port>` (helm/templates/deployment-cache-server.yaml:
+ * 62-65) and gives every engine LMCACHE_REMOTE_URL=lm://<service>:<port> with
+ * LMCACHE_REMOTE_SERDE naive|cachegen (helm/templates/deployment-vllm-multi.yaml:338-345,
+ * helm/tests/lmcache_test.yaml:166-181).  The server keeps chunks in a b200kv pool of
+ * `pool_bytes`, created by the first PUT with the clients' slot size; the client moves a
+ * chunk between the socket and a slot of the LOCAL pinned pool directly, so a fetched chunk
+ * is loadable by b200kv_load_async at once.  Own wire format (48-byte header + payload);
+ * LMCache's is not available here — parity unpinned.  A `b200kv_remote` is one connection;
+ * calls on it are serialised internally.                                                   */
+typedef struct b200kv_server b200kv_server;
+typedef struct b200kv_remote b200kv_remote;
+/* host NULL/"0.0.0.0" = any; port 0 = pick one (read it back with b200kv_server_port).     */
+int b200kv_server_start(const char* host, int port, uint64_t pool_bytes, b200kv_server** out);
+int b200kv_server_port(b200kv_server* srv);
+/* out5 = {chunks put, chunks served, get misses, payload bytes in, payload bytes out}.     */
+int b200kv_server_get_stats(b200kv_server* srv, uint64_t* out5);
+int b200kv_server_stop(b200kv_server* srv);
+
+int b200kv_remote_connect(const char* host, int port, int timeout_ms, b200kv_remote** out);
+int b200kv_remote_close(b200kv_remote* r);
+int b200kv_remote_ping(b200kv_remote* r);
+/* *n_prefix = how many leading keys the server holds (longest stored prefix, like lookup). */
+int b200kv_remote_exists(b200kv_remote* r, const uint64_t* keys, int32_t n_keys, int32_t* n_prefix);
+/* Local pool -> server.  -ENOENT: not READY locally; -EEXIST: server has it (nothing sent). */
+int b200kv_remote_put(b200kv_remote* r, b200kv_pool* local, uint64_t key, uint32_t owner);
+/* Server -> local pool (reserve / receive into the slot / commit).  OK if already local.   */
+int b200kv_remote_get(b200kv_remote* r, b200kv_pool* local, uint64_t key, uint32_t owner);
+int b200kv_remote_stats(b200kv_remote* r, b200kv_pool_stats* out);
+int b200kv_remote_traffic(b200kv_remote* r, uint64_t* bytes_up, uint64_t* bytes_down);
 
 #ifdef __cplusplus
 }

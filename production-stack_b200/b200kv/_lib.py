@@ -104,6 +104,18 @@ SIGNATURES = {
     "b200kv_peer_pull_async": (C.c_int, [_P, C.c_int32, _I64P, _I64P, C.c_int64, _P, _U64P]),
     "b200kv_engine_get_stats": (C.c_int, [_P, C.POINTER(EngineStats)]),
     "b200kv_last_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
+    "b200kv_server_start": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_P)]),
+    "b200kv_server_port": (C.c_int, [_P]),
+    "b200kv_server_get_stats": (C.c_int, [_P, _U64P]),
+    "b200kv_server_stop": (C.c_int, [_P]),
+    "b200kv_remote_connect": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
+    "b200kv_remote_close": (C.c_int, [_P]),
+    "b200kv_remote_ping": (C.c_int, [_P]),
+    "b200kv_remote_exists": (C.c_int, [_P, _U64P, C.c_int32, _I32P]),
+    "b200kv_remote_put": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32]),
+    "b200kv_remote_get": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32]),
+    "b200kv_remote_stats": (C.c_int, [_P, C.POINTER(PoolStats)]),
+    "b200kv_remote_traffic": (C.c_int, [_P, _U64P, _U64P]),
 }
 
 _lib = None

@@ -253,6 +253,7 @@ class WorkerState:
         self.async_loads: list[tuple[int, str]] = []   # (ticket, req_id) of detached loads in flight
         # layer-wise loads of the current step: (ticket, blocks it fills); the forward pass waits per layer
         self.layer_loads: list[tuple[int, list[int]]] = []
+        self.on_stored = None    # callable(chunk keys) after a store was issued (remote tier upload)
         self.stats = WorkerStats()
 
     def start_load(self, metas: list[ReqMeta], stream=None, layers_per_group: int = 0):
@@ -345,6 +346,11 @@ class WorkerState:
             if ticket:
                 self.pending_tickets.append(ticket)
             self.stats.num_stored_tokens += n - lead
+            if self.on_stored is not None:
+                try:
+                    self.on_stored(self.engine._keys(tokens[:n])[lead // self.chunk:])
+                except Exception as e:
+                    logger.error("b200kv: remote upload hook failed for %s: %s", m.req_id, e)
             ss.skip_leading_tokens = n
 
     def wait_layer(self, layer: int, stream=None):

@@ -16,7 +16,7 @@ logger = logging.getLogger("b200kv")
 _TRUE = {"1", "true", "yes", "on"}
 
 # accepted for compatibility but without effect here (out of scope rows of SURVEY.md Appendix A)
-_IGNORED = ("LMCACHE_MAX_LOCAL_DISK_SIZE", "LMCACHE_LOCAL_DISK", "LMCACHE_REMOTE_URL",
+_IGNORED = ("LMCACHE_MAX_LOCAL_DISK_SIZE", "LMCACHE_LOCAL_DISK",
             "LMCACHE_ENABLE_NIXL", "LMCACHE_NIXL_ROLE", "LMCACHE_USE_EXPERIMENTAL")
 
 
@@ -47,6 +47,8 @@ class B200KVConfig:
     layerwise: bool = True                # B200KV_LAYERWISE / LMCACHE_USE_LAYERWISE: per-layer-group loads (default on:
                                           # TTFT 24.4 -> 19.3 ms, outputs identical; profiles/e2e_mrqa_r01.json)
     layer_group: int = 4                  # B200KV_LAYER_GROUP: layers per group
+    remote_url: str | None = None         # LMCACHE_REMOTE_URL=lm://host:port: cache-server tier (b200kv/remote.py)
+    remote_wait_ms: int = 2000            # B200KV_REMOTE_WAIT_MS: longest a request waits for its remote prefetch
     extra: dict = field(default_factory=dict)
 
     @staticmethod
@@ -87,6 +89,8 @@ class B200KVConfig:
         c.async_load = _b(e.get("B200KV_ASYNC_LOAD"), False)
         c.layerwise = _b(e.get("B200KV_LAYERWISE", e.get("LMCACHE_USE_LAYERWISE")), True)
         c.layer_group = max(1, int(e.get("B200KV_LAYER_GROUP", c.layer_group)))
+        c.remote_url = e.get("LMCACHE_REMOTE_URL") or None
+        c.remote_wait_ms = int(e.get("B200KV_REMOTE_WAIT_MS", c.remote_wait_ms))
         for k in _IGNORED:
             if e.get(k) not in (None, "", "0", "False", "false"):
                 logger.warning("%s=%s is accepted for chart compatibility but has no effect in b200kv", k, e.get(k))

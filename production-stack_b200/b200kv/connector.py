@@ -121,6 +121,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._pd: PDScheduler | None = None
         self._pdw: PDWorker | None = None
         self._remote_computed: dict[str, int] = {}
+        self._remote = None     # cache-server tier (LMCACHE_REMOTE_URL), b200kv/remote.py
         if role == KVConnectorRole.SCHEDULER:
             self._pd = PDScheduler(self._engine_id, self._block_size,
                                    lease_s=float(self.cfg.extra.get("pd_lease_s", 120.0)))
@@ -135,9 +136,22 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
 
             self._sched = SchedulerState(lookup, self._block_size, self._chunk, self._discard_partial,
                                          self.cfg.save_decode_cache, self.kv_role, async_load=self.cfg.async_load)
+            if self.kv_role != "kv_producer":     # the scheduler fetches every TP rank's chunks of a prompt
+                self._remote = self._make_remote([self._key_seed(r) for r in range(self._world)])
         logger.info("b200kv connector role=%s kv_role=%s pool=%s (%.1f GB, chunk %d, fmt %s)",
                     role.name, self.kv_role, self._pool_name, self.cfg.max_local_cpu_size_gb, self._chunk,
                     "fp8" if self.cfg.fmt else "raw")
+
+    def _make_remote(self, key_seeds):
+        """LMCACHE_REMOTE_URL=lm://host:port (deployment-vllm-multi.yaml:338-345): the cache-server
+        tier behind the local pinned pool.  A malformed URL is a fatal misconfiguration."""
+        from .remote import RemoteTier, parse_remote_url
+        hp = parse_remote_url(self.cfg.remote_url)
+        if hp is None:
+            return None
+        logger.info("b200kv remote tier: %s:%d", *hp)
+        return RemoteTier(self._pool, hp[0], hp[1], self._chunk, key_seeds, owner=owner_tag_of(self.cfg.instance_id),
+                          include_partial=not self._discard_partial, wait_s=self.cfg.remote_wait_ms / 1e3)
 
     def _key_seed(self, rank: int) -> int:
         """Same namespace in both roles: derived from the vLLM config only (the tile layout is a
@@ -177,6 +191,10 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._layer_hooks_seen = 0
         self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role,
                                    owner_tag=owner_tag_of(self.cfg.instance_id) if self.cfg.pool_name else 0)
+        if self.kv_role != "kv_consumer":
+            self._remote = self._make_remote(self._engine.key_seed)
+            if self._remote is not None:
+                self._worker.on_stored = self._remote.push     # upload what this worker stores
         try:
             publish_ipc(self._engine_id, self._engine, t0.device.index or 0)   # peers may pull from us
             self._pdw = PDWorker(self._engine, self._engine_id, self._block_size)
@@ -294,6 +312,9 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         return B200KVPromMetrics(vllm_config, metric_types, labelnames, per_engine_labelvalues)
 
     def shutdown(self):
+        if self._remote is not None:
+            self._remote.close()
+            self._remote = None
         if self._controller is not None:
             self._controller.close()
             self._controller = None
@@ -316,6 +337,9 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         if remote is not None:   # decode side of a disaggregated request: pull from the prefiller
             self._remote_computed[request.request_id] = num_computed_tokens
             return remote, False
+        if self._remote is not None and self._remote.prefetch_state(
+                request.request_id, request.prompt_token_ids or []) == self._remote.PENDING:
+            return None, False   # chunks are on their way from the cache server: ask again next step
         n = self._sched.num_new_matched_tokens(request.request_id, request.prompt_token_ids or [],
                                                request.num_tokens, num_computed_tokens)
         return n, bool(self._sched.async_load and n > 0)
@@ -341,6 +365,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         # Offload: the gather that reads a request's pages is ordered before any later forward pass
         # on the compute stream, so blocks may be freed immediately.  Disaggregated prefill: keep
         # the pages (delay_free) until the decoder has pulled them (b200kv/pd.py).
+        if self._remote is not None:
+            self._remote.forget(request.request_id)
         if self._pd is not None:
             ok = True
             st = getattr(request, "status", None)

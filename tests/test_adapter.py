@@ -281,3 +281,34 @@ def test_foreign_tokens_counts_chunks_of_other_owners(shm_name):
     assert WorkerState(eng, BS, C, owner_tag=22)._foreign_tokens(toks, 0, len(toks)) == C + 10
     pool.close()
     KVPool.unlink(shm_name)
+
+
+def test_on_stored_hook_gets_the_new_chunk_keys_only():
+    """Remote tier upload hook: after each store the worker hands over the keys of exactly the chunks
+    this store added (not the leading ones an earlier step already saved)."""
+    from b200kv.engine import chunk_keys
+
+    eng = OracleBackedEngine([np.zeros((2, 64, BS, 1, 8), np.uint16)])
+    eng._keys = lambda t: chunk_keys(t, C, 99, True)
+    sched = SchedulerState(lambda t: 0, BS, C, False)
+    w = WorkerState(eng, BS, C)
+    seen = []
+    w.on_stored = lambda keys: seen.append([int(k) for k in keys])
+    prompt = list(range(1, 3 * C + 21))
+    want = [int(k) for k in chunk_keys(np.asarray(prompt, np.int32), C, 99, True)]
+    req = NS(request_id="q", prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt)
+    sched.num_new_matched_tokens("q", prompt, len(prompt), 0)
+    sched.after_alloc(req, 0)
+    w.save(sched.build_meta(sched_out([new_req("q", prompt, list(range(7)))], num_sched={"q": 100})))
+    cached = NS(req_ids=["q"], new_block_ids=[(list(range(7, 14)),)], resumed_req_ids=set(), all_token_ids={})
+    w.save(sched.build_meta(sched_out(cached=cached, num_sched={"q": 100})))
+    assert seen == [want[:1], want[1:3]]
+    w.on_stored = lambda keys: 1 / 0          # a failing hook never fails the step
+    w2 = WorkerState(eng, BS, C)
+    w2.on_stored = w.on_stored
+    p2 = list(range(500, 500 + C))
+    r2 = NS(request_id="z", prompt_token_ids=p2, num_tokens=C, all_token_ids=p2)
+    sched.num_new_matched_tokens("z", p2, C, 0)
+    sched.after_alloc(r2, 0)
+    w2.save(sched.build_meta(sched_out([new_req("z", p2, list(range(20, 24)))], num_sched={"z": C})))
+    assert eng.calls[-1] == ("store", C, 0)

@@ -156,3 +156,57 @@ def test_config_file_and_per_request_skip_save(tmp_path):
     out = NS(scheduled_new_reqs=[req], scheduled_cached_reqs=NS(req_ids=[], new_block_ids=[], resumed_req_ids=set(), all_token_ids={}),
              num_scheduled_tokens={"r": 300}, finished_req_ids=set())
     assert sched.build_meta(out) == []                                                 # nothing saved, nothing loaded
+
+
+def test_scheduler_waits_for_remote_prefetch_then_hits(monkeypatch):
+    """LMCACHE_REMOTE_URL=lm://...: a prompt whose chunks sit only on the cache server makes
+    get_num_new_matched_tokens answer (None, False) — vLLM's "ask again" — until they have landed in
+    the LOCAL pool; afterwards it is an ordinary local hit (helm/templates/deployment-vllm-multi.yaml:
+    338-345; KVConnectorBase_V1.get_num_new_matched_tokens, base.py:453-486)."""
+    import time
+
+    from vllm.distributed.kv_transfer.kv_connector.v1.base import KVConnectorRole
+
+    from b200kv import KVPool, _lib, chunk_keys
+    from b200kv.connector import B200KVConnector, geometry_from_vllm
+    from b200kv.remote import RemoteClient, RemoteServer
+    srv = RemoteServer("127.0.0.1", 0, 64 << 20)
+    monkeypatch.setenv("LMCACHE_MAX_LOCAL_CPU_SIZE", "0.05")
+    monkeypatch.setenv("LMCACHE_CHUNK_SIZE", "64")
+    monkeypatch.setenv("B200KV_ASYNC_LOAD", "0")
+    monkeypatch.setenv("LMCACHE_REMOTE_URL", f"lm://127.0.0.1:{srv.port}")
+    cfg = fake_vllm_config(f"t{os.getpid()}r{os.urandom(3).hex()}")
+    conn = B200KVConnector(cfg, KVConnectorRole.SCHEDULER, None)
+    try:
+        geom = geometry_from_vllm(cfg, conn.cfg)
+        prompt = list(range(200))
+        keys = chunk_keys(np.asarray(prompt, np.int32), 64, geom.key_seed("synth-llama", 1, 0))
+        # another replica stored chunks 0..2 and uploaded them
+        other = KVPool(None, 8 * geom.chunk_bytes, geom.chunk_bytes, _lib.POOL_CREATE)
+        c = RemoteClient("127.0.0.1", srv.port)
+        for i, k in enumerate(keys[:3]):
+            slot = other.reserve(int(k), 64, 0, 5)
+            other.slot_view(slot)[:] = i + 1
+            other.commit(int(k))
+            assert c.put(other, int(k), 5) == 0
+        req = NS(request_id="r1", prompt_token_ids=prompt, num_tokens=200, all_token_ids=prompt)
+        assert conn.get_num_new_matched_tokens(req, 0) == (None, False)
+        t0 = time.time()
+        while True:
+            n, is_async = conn.get_num_new_matched_tokens(req, 0)
+            if n is not None:
+                break
+            assert time.time() - t0 < 10
+            time.sleep(0.005)
+        assert (n, is_async) == (192, False)
+        slot, n_tok, fmt = conn._pool.acquire(int(keys[1]))
+        assert n_tok == 64 and int(conn._pool.slot_view(slot)[0]) == 2     # the bytes the other replica stored
+        conn._pool.release(int(keys[1]))
+        assert conn.get_num_new_matched_tokens(req, 0) == (192, False)     # local now: answered at once
+        assert conn.request_finished(req, []) == (False, None)
+        c.close()
+        other.close()
+    finally:
+        conn.shutdown()
+        KVPool.unlink(conn._pool_name)
+        srv.stop()
