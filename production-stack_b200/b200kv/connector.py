@@ -64,6 +64,9 @@ def _traced(fn):
 class B200KVConnectorMetadata(KVConnectorMetadata):
     requests: list[ReqMeta] = field(default_factory=list)
     pd: PDMeta = field(default_factory=PDMeta)   # disaggregated-prefill pulls / held requests
+    # this engine's cumulative (lookups, hit tokens, requested tokens): the worker reports them as the
+    # lmcache:* series, so replicas sharing one pool each report their own traffic, not the box's
+    sched_counters: tuple = (0, 0, 0)
 
 
 def geometry_from_vllm(vllm_config, cfg: B200KVConfig, n_blocks: int = 1) -> KVGeometry:
@@ -122,6 +125,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._pdw: PDWorker | None = None
         self._remote_computed: dict[str, int] = {}
         self._remote = None     # cache-server tier (LMCACHE_REMOTE_URL), b200kv/remote.py
+        self._sched_counters: tuple = (0, 0, 0)   # worker: last counters received from this engine's scheduler
         if role == KVConnectorRole.SCHEDULER:
             self._pd = PDScheduler(self._engine_id, self._block_size,
                                    lease_s=float(self.cfg.extra.get("pd_lease_s", 120.0)))
@@ -183,6 +187,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             raise ValueError("KV cache tensors do not match the model geometry the pool was sized for "
                              f"({geom.chunk_bytes} vs {geom0.chunk_bytes} bytes per chunk)")
         rank = getattr(self._vllm_config.parallel_config, "rank", 0)
+        self._rank = rank
         self._engine = KVEngine(geom, self._pool, device=t0.device.index or 0,
                                 staging_bytes=self.cfg.staging_mb << 20, owner=owner_tag_of(self.cfg.instance_id),
                                 variant=self.cfg.variant, key_seed=self._key_seed(rank))
@@ -219,6 +224,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             return
         stream = torch.cuda.current_stream()
         md = self._get_connector_metadata()
+        if isinstance(md, B200KVConnectorMetadata) and md.sched_counters[0] >= self._sched_counters[0]:
+            self._sched_counters = tuple(md.sched_counters)
         if self._pdw is not None and isinstance(md, B200KVConnectorMetadata) and (md.pd.pulls or md.pd.held):
             self._pdw.start_pulls(md.pd, stream=stream)
         self._layer_hooks_seen = 0
@@ -289,7 +296,9 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         cur = {"num_stored_tokens": ws.num_stored_tokens, "num_loaded_tokens": ws.num_loaded_tokens,
                "retrieve_seconds": ws.retrieve_seconds, "retrieve_calls": ws.retrieve_calls,
                "load_shortfalls": ws.num_load_shortfalls, "num_foreign_loaded_tokens": ws.num_foreign_loaded_tokens,
-               "num_hit_tokens": ps["n_hit_tokens"], "num_requested_tokens": ps["n_requested_tokens"],
+               # the scheduler's counters are per engine, not per TP rank: rank 0 reports them
+               "num_hit_tokens": self._sched_counters[1] if getattr(self, "_rank", 0) == 0 else 0,
+               "num_requested_tokens": self._sched_counters[2] if getattr(self, "_rank", 0) == 0 else 0,
                "retrieve_bytes": ws.num_loaded_tokens * self._engine.geom.payload_bytes_per_token,
                "store_bytes": ws.num_stored_tokens * self._engine.geom.payload_bytes_per_token}
         prev = getattr(self, "_stats_prev", {})
@@ -358,7 +367,9 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
     @_traced
     def build_connector_meta(self, scheduler_output: "SchedulerOutput") -> KVConnectorMetadata:
         assert self._sched is not None and self._pd is not None
-        return B200KVConnectorMetadata(self._sched.build_meta(scheduler_output), self._pd.build_meta())
+        sc = self._sched
+        return B200KVConnectorMetadata(sc.build_meta(scheduler_output), self._pd.build_meta(),
+                                       (sc.num_lookups, sc.num_hit_tokens, sc.num_requested_tokens))
 
     @_traced
     def request_finished(self, request: "Request", block_ids: list[int]) -> tuple[bool, dict[str, Any] | None]:

@@ -70,6 +70,8 @@ def test_scheduler_role_lookup_and_metadata(monkeypatch):
         assert m.load_spec.can_load and m.load_spec.external_cached_tokens == 128 and m.load_spec.vllm_cached_tokens == 64
         import pickle
         assert pickle.loads(pickle.dumps(meta)).requests[0].block_ids == list(range(13))   # crosses processes
+        # this engine's own lookup traffic rides along (3 lookups of a 200-token prompt: 0 + 128 + 128 hit)
+        assert pickle.loads(pickle.dumps(meta)).sched_counters == (3, 256, 600)
         assert conn.request_finished(req, []) == (False, None)
         assert conn.request_finished_all_groups(req, ([],)) == (False, None)
     finally:

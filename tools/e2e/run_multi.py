@@ -13,6 +13,9 @@ Modes:
   private    connector, one pool per replica -> a turn hits only if it lands where its history was stored
   shared     connector, one pool per box     -> any replica retrieves what any other stored (one PCIe hop)
   shared8    shared, FP8 packed format
+  remote     connector, one pool per replica + the cache-server tier (`python -m b200kv.server`,
+             LMCACHE_REMOTE_URL=lm://127.0.0.1:8095): a turn that lands on the other replica is fetched
+             from the server into the local pinned pool, then loaded
 
     python tools/e2e/run_multi.py --replicas 2 --routing roundrobin --modes none,private,shared
 """
@@ -55,6 +58,8 @@ def replica_env(mode: str, gpu: int, cpu_gb: float, pool_tag: str) -> tuple[dict
                LMCACHE_LMCACHE_INSTANCE_ID=f"replica-{gpu}")
     if mode.startswith("shared"):
         env["B200KV_POOL_NAME"] = f"/b200kv-box-{pool_tag}"
+    if mode.startswith("remote"):
+        env["LMCACHE_REMOTE_URL"] = "lm://127.0.0.1:8095"
     cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}
     return env, ["--kv-transfer-config", json.dumps(cfg)]
 
@@ -114,6 +119,14 @@ def main():
         res = {"mode": mode, "same_gpu": args.same_gpu, "replicas": args.replicas, "routing": args.routing, "router": rpath}
         try:
             ports = [8100 + i for i in range(args.replicas)]
+            if mode.startswith("remote"):
+                senv = dict(os.environ, B200KV_SERVER_GB=str(args.cpu_gb * args.replicas),
+                            PYTHONPATH=os.path.join(ROOT, "production-stack_b200") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+                slog = open(os.path.join(args.log_dir, f"cache_server_{mode}.log"), "w")
+                logs.append(slog)
+                procs.append(subprocess.Popen([sys.executable, "-m", "b200kv.server", "127.0.0.1", "8095"], env=senv,
+                                              stdout=slog, stderr=subprocess.STDOUT, start_new_session=True))
+            n_aux = len(procs)
             for i, port in enumerate(ports):
                 gb = args.cpu_gb * (args.replicas if mode.startswith("shared") else 1)
                 env, cargs = replica_env(mode, 0 if args.same_gpu else i, gb, f"{os.getpid()}-{mode}")
@@ -132,7 +145,8 @@ def main():
                 if args.same_gpu and not wait_ready(port, procs[-1], args.startup_timeout):
                     break
             res["startup_s"] = time.time() - t_mode
-            if len(procs) != len(ports) or not all(wait_ready(p, pr, args.startup_timeout) for p, pr in zip(ports, procs)):
+            engines = procs[n_aux:]
+            if len(engines) != len(ports) or not all(wait_ready(p, pr, args.startup_timeout) for p, pr in zip(ports, engines)):
                 res["error"] = "replicas not ready"
                 continue
             renv = dict(os.environ)
