@@ -126,6 +126,8 @@ typedef struct b200kv_pool_stats {
   uint64_t n_lookups, n_lookup_chunks, n_hit_chunks;     /* lmcache:num_requested/hit_tokens  */
   uint64_t n_hit_tokens, n_requested_tokens;             /*   (helm/dashboards/lmcache-…json) */
   uint64_t n_stored_chunks, n_evicted_chunks, n_dropped_chunks;
+  uint64_t n_reclaimed_chunks; /* slots / pins taken back from writers / readers that died        */
+  uint64_t n_recoveries;       /* index rebuilt after a process died holding the pool lock       */
 } b200kv_pool_stats;
 
 int b200kv_pool_open(const b200kv_pool_config* cfg, b200kv_pool** out);
@@ -158,6 +160,13 @@ int b200kv_pool_acquire(b200kv_pool* pool, uint64_t key, uint32_t* slot_out,
                         int32_t* n_tokens_out, uint32_t* fmt_out);
 int b200kv_pool_release(b200kv_pool* pool, uint64_t key);
 int b200kv_pool_get_stats(b200kv_pool* pool, b200kv_pool_stats* out);
+/* Failure detection.  A process that dies between reserve and commit, or between acquire and
+ * release, leaves a WRITING slot / a pin behind: both are taken back once older than
+ * B200KV_POOL_STALE_MS (default 120 s; age, not pid — replicas may live in different pid
+ * namespaces).  A process that dies while holding the pool lock triggers a rebuild of the free
+ * list, LRU list and hash table from the slot array on the next call of any process.
+ * b200kv_pool_check verifies those structures against the slot array (0, or -EIO).          */
+int b200kv_pool_check(b200kv_pool* pool);
 int b200kv_pool_clear(b200kv_pool* pool); /* KVConnectorBase_V1.reset_cache               */
 
 /* ======================================================================================= */

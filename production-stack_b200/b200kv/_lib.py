@@ -29,7 +29,7 @@ class PoolStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_slots", "n_used", "slot_bytes", "n_lookups", "n_lookup_chunks", "n_hit_chunks",
         "n_hit_tokens", "n_requested_tokens", "n_stored_chunks", "n_evicted_chunks",
-        "n_dropped_chunks")]
+        "n_dropped_chunks", "n_reclaimed_chunks", "n_recoveries")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -85,6 +85,7 @@ SIGNATURES = {
     "b200kv_pool_release": (C.c_int, [_P, C.c_uint64]),
     "b200kv_pool_get_stats": (C.c_int, [_P, C.POINTER(PoolStats)]),
     "b200kv_pool_clear": (C.c_int, [_P]),
+    "b200kv_pool_check": (C.c_int, [_P]),
     "b200kv_engine_create": (C.c_int, [C.POINTER(EngineConfig), _P, C.POINTER(_P)]),
     "b200kv_engine_destroy": (C.c_int, [_P]),
     "b200kv_engine_chunk_bytes": (C.c_int64, [C.POINTER(EngineConfig)]),

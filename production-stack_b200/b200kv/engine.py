@@ -186,6 +186,10 @@ class KVPool:
         check(lib().b200kv_pool_get_stats(self.handle, C.byref(s)), "b200kv_pool_get_stats")
         return s.as_dict()
 
+    def check(self) -> bool:
+        """Index / LRU / free list consistent with the slot array (b200kv_pool_check)."""
+        return lib().b200kv_pool_check(self.handle) == 0
+
     def clear(self) -> bool:
         rc = lib().b200kv_pool_clear(self.handle)
         if rc == _lib.EBUSY:

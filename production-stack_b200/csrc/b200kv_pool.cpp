@@ -27,7 +27,7 @@
 namespace {
 
 constexpr uint64_t kMagic = 0x6232303030304b56ull;  // "b20000KV"
-constexpr uint32_t kVersion = 1;
+constexpr uint32_t kVersion = 2;
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr uint32_t kTomb = 0xfffffffeu;
 constexpr uint32_t kEmpty = 0;  // bucket value = slot index + 1
@@ -44,6 +44,9 @@ struct Slot {
   uint32_t pins;
   uint32_t lru_prev, lru_next;  // READY slots, oldest at head
   uint32_t free_next;
+  uint32_t pad;
+  uint64_t touched_ns;  // reserve time (WRITING) / last acquire (pins): a writer or reader that died
+                        // is recognised by age, not by pid (replicas may sit in different pid namespaces)
 };
 
 struct PoolHeader {
@@ -89,11 +92,19 @@ struct b200kv_pool {
   bool creator = false;
   char name[256] = {0};
 
+  uint64_t stale_ns = 120ull * 1000000000ull;  // B200KV_POOL_STALE_MS
+  uint64_t die_key = 0;  // fault injection (tests): _exit inside the critical section of reserve(die_key)
+
   struct Guard {
     PoolHeader* h;
-    explicit Guard(PoolHeader* hh) : h(hh) {
+    explicit Guard(b200kv_pool* p) : h(p->h) {
       int rc = pthread_mutex_lock(&h->mu);
-      if (rc == EOWNERDEAD) pthread_mutex_consistent(&h->mu);  // a holder died; state is ours
+      if (rc == EOWNERDEAD) {
+        // A process died inside a critical section: lists and table may be half-updated.  Slot
+        // states and keys are written last-writer-wins and are the ground truth; rebuild the rest.
+        p->recover();
+        pthread_mutex_consistent(&h->mu);
+      }
     }
     ~Guard() { pthread_mutex_unlock(&h->mu); }
   };
@@ -162,25 +173,80 @@ struct b200kv_pool {
     h->free_head = s;
     --h->n_used;
   }
-  uint32_t take_slot() {  // free list first, then LRU eviction
-    if (h->free_head != kNone) {
-      const uint32_t s = h->free_head;
-      h->free_head = slots[s].free_next;
-      return s;
-    }
+  bool stale(const Slot& e, uint64_t t) const { return t > e.touched_ns && t - e.touched_ns > stale_ns; }
+  uint32_t pop_free() {
+    const uint32_t s = h->free_head;
+    h->free_head = slots[s].free_next;
+    return s;
+  }
+  uint32_t take_slot() {  // free list first, then LRU eviction, then slots abandoned by dead processes
+    if (h->free_head != kNone) return pop_free();
     const uint64_t t = now_ns();
     for (uint32_t s = h->lru_head; s != kNone; s = slots[s].lru_next) {
       Slot& e = slots[s];
+      if (e.pins && stale(e, t)) {  // a reader died between acquire and release
+        e.pins = 0;
+        ++h->stats.n_reclaimed_chunks;
+      }
       if (e.pins == 0 && e.lease_until_ns <= t) {
         lru_unlink(s);
         free_slot(s);
         ++h->stats.n_evicted_chunks;
-        const uint32_t got = h->free_head;
-        h->free_head = slots[got].free_next;
-        return got;
+        return pop_free();
+      }
+    }
+    for (uint32_t s = 0; s < h->n_slots; ++s) {  // a writer died between reserve and commit
+      if (slots[s].state == kWriting && stale(slots[s], t)) {
+        free_slot(s);
+        ++h->stats.n_reclaimed_chunks;
+        return pop_free();
       }
     }
     return kNone;
+  }
+  // Rebuild every derived structure from the slot array (after EOWNERDEAD).
+  void recover() {
+    h->free_head = kNone;
+    h->lru_head = h->lru_tail = kNone;
+    h->n_used = 0;
+    for (uint32_t s = h->n_slots; s-- > 0;) {
+      Slot& e = slots[s];
+      if (e.state != kWriting && e.state != kReady) e.state = kFree;
+      e.lru_prev = e.lru_next = kNone;
+      if (e.state == kFree) {
+        e.pins = 0;
+        e.lease_until_ns = 0;
+        e.free_next = h->free_head;
+        h->free_head = s;
+      } else {
+        ++h->n_used;
+      }
+    }
+    // duplicates of one key cannot both be kept (a reserve died after writing the second): keep READY
+    rebuild_dedup();
+    for (uint32_t s = 0; s < h->n_slots; ++s)
+      if (slots[s].state == kReady) lru_push_tail(s);
+    ++h->stats.n_recoveries;
+  }
+  void rebuild_dedup() {
+    std::memset(table, 0, sizeof(uint32_t) * h->table_cap);
+    h->n_tombs = 0;
+    for (int pass = 0; pass < 2; ++pass) {  // READY first, so a WRITING twin loses
+      for (uint32_t s = 0; s < h->n_slots; ++s) {
+        Slot& e = slots[s];
+        if (e.state != (pass == 0 ? kReady : kWriting)) continue;
+        if (find(e.key) != kNone) {
+          e.state = kFree;
+          e.pins = 0;
+          e.lease_until_ns = 0;
+          e.free_next = h->free_head;
+          h->free_head = s;
+          --h->n_used;
+          continue;
+        }
+        table_insert(s);
+      }
+    }
   }
 };
 
@@ -243,6 +309,11 @@ extern "C" int b200kv_pool_open(const b200kv_pool_config* cfg, b200kv_pool** out
 
   b200kv_pool* p = new (std::nothrow) b200kv_pool();
   if (!p) return B200KV_ENOMEM;
+  if (const char* e = getenv("B200KV_POOL_STALE_MS")) {
+    const long long ms = atoll(e);
+    if (ms > 0) p->stale_ns = static_cast<uint64_t>(ms) * 1000000ull;
+  }
+  if (const char* e = getenv("B200KV_POOL_TEST_DIE_KEY")) p->die_key = strtoull(e, nullptr, 10);
 
   int fd = -1;
   bool creating = false;
@@ -398,7 +469,7 @@ extern "C" int b200kv_pool_lookup(b200kv_pool* pool, const uint64_t* keys,
                                   uint32_t lease_ms, int32_t* n_hit_chunks,
                                   int64_t* n_hit_tokens) {
   if (!pool || n_keys < 0 || (n_keys > 0 && (!keys || !chunk_tokens))) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   const uint64_t lease = now_ns() + static_cast<uint64_t>(lease_ms) * 1000000ull;
   int32_t hits = 0;
   int64_t toks = 0, req = 0;
@@ -427,7 +498,7 @@ extern "C" int b200kv_pool_lookup(b200kv_pool* pool, const uint64_t* keys,
 extern "C" int b200kv_pool_lookup_owner(b200kv_pool* pool, const uint64_t* keys, int32_t n_keys,
                                         int32_t* n_hit_chunks, uint32_t* owner_out) {
   if (!pool || n_keys < 0 || (n_keys > 0 && !keys)) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   int32_t hits = 0;
   for (int32_t i = 0; i < n_keys; ++i) {
     const uint32_t s = pool->find(keys[i]);
@@ -442,8 +513,14 @@ extern "C" int b200kv_pool_lookup_owner(b200kv_pool* pool, const uint64_t* keys,
 extern "C" int b200kv_pool_reserve(b200kv_pool* pool, uint64_t key, int32_t n_tokens,
                                    uint32_t fmt, uint32_t owner, uint32_t* slot_out) {
   if (!pool || !slot_out || n_tokens <= 0) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
-  if (pool->find(key) != kNone) return B200KV_EEXIST;
+  b200kv_pool::Guard g(pool);
+  const uint32_t twin = pool->find(key);
+  if (twin != kNone) {
+    Slot& t = pool->slots[twin];
+    if (t.state != kWriting || !pool->stale(t, now_ns())) return B200KV_EEXIST;
+    pool->free_slot(twin);  // its writer died long ago: take the key over
+    ++pool->h->stats.n_reclaimed_chunks;
+  }
   const uint32_t s = pool->take_slot();
   if (s == kNone) {
     ++pool->h->stats.n_dropped_chunks;
@@ -457,8 +534,10 @@ extern "C" int b200kv_pool_reserve(b200kv_pool* pool, uint64_t key, int32_t n_to
   e.owner = owner;
   e.pins = 0;
   e.lease_until_ns = 0;
+  e.touched_ns = now_ns();
   e.lru_prev = e.lru_next = kNone;
   pool->table_insert(s);
+  if (pool->die_key && key == pool->die_key) _exit(9);  // lock held, n_used not yet updated
   ++pool->h->n_used;
   *slot_out = s;
   return B200KV_OK;
@@ -466,7 +545,7 @@ extern "C" int b200kv_pool_reserve(b200kv_pool* pool, uint64_t key, int32_t n_to
 
 extern "C" int b200kv_pool_commit(b200kv_pool* pool, uint64_t key) {
   if (!pool) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   const uint32_t s = pool->find(key);
   if (s == kNone || pool->slots[s].state != kWriting) return B200KV_ENOENT;
   pool->slots[s].state = kReady;
@@ -477,7 +556,7 @@ extern "C" int b200kv_pool_commit(b200kv_pool* pool, uint64_t key) {
 
 extern "C" int b200kv_pool_abort(b200kv_pool* pool, uint64_t key) {
   if (!pool) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   const uint32_t s = pool->find(key);
   if (s == kNone || pool->slots[s].state != kWriting) return B200KV_ENOENT;
   pool->free_slot(s);
@@ -487,11 +566,12 @@ extern "C" int b200kv_pool_abort(b200kv_pool* pool, uint64_t key) {
 extern "C" int b200kv_pool_acquire(b200kv_pool* pool, uint64_t key, uint32_t* slot_out,
                                    int32_t* n_tokens_out, uint32_t* fmt_out) {
   if (!pool || !slot_out) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   const uint32_t s = pool->find(key);
   if (s == kNone || pool->slots[s].state != kReady) return B200KV_ENOENT;
   Slot& e = pool->slots[s];
   ++e.pins;
+  e.touched_ns = now_ns();
   pool->lru_unlink(s);
   pool->lru_push_tail(s);
   *slot_out = s;
@@ -502,7 +582,7 @@ extern "C" int b200kv_pool_acquire(b200kv_pool* pool, uint64_t key, uint32_t* sl
 
 extern "C" int b200kv_pool_release(b200kv_pool* pool, uint64_t key) {
   if (!pool) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   const uint32_t s = pool->find(key);
   if (s == kNone || pool->slots[s].state != kReady || pool->slots[s].pins == 0)
     return B200KV_ENOENT;
@@ -512,7 +592,7 @@ extern "C" int b200kv_pool_release(b200kv_pool* pool, uint64_t key) {
 
 extern "C" int b200kv_pool_get_stats(b200kv_pool* pool, b200kv_pool_stats* out) {
   if (!pool || !out) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   *out = pool->h->stats;
   out->n_slots = pool->h->n_slots;
   out->n_used = pool->h->n_used;
@@ -520,9 +600,33 @@ extern "C" int b200kv_pool_get_stats(b200kv_pool* pool, b200kv_pool_stats* out) 
   return B200KV_OK;
 }
 
+extern "C" int b200kv_pool_check(b200kv_pool* pool) {
+  if (!pool) return B200KV_EINVAL;
+  b200kv_pool::Guard g(pool);
+  const uint32_t n = pool->h->n_slots;
+  uint32_t n_free = 0, n_ready = 0, n_writing = 0, walked = 0;
+  for (uint32_t s = 0; s < n; ++s) {
+    const uint32_t st = pool->slots[s].state;
+    n_free += st == kFree;
+    n_ready += st == kReady;
+    n_writing += st == kWriting;
+    if (st != kFree && pool->find(pool->slots[s].key) != s) return B200KV_EIO;  // not (uniquely) indexed
+  }
+  if (n_free + n_ready + n_writing != n || pool->h->n_used != n_ready + n_writing) return B200KV_EIO;
+  for (uint32_t s = pool->h->free_head; s != kNone; s = pool->slots[s].free_next)
+    if (++walked > n || pool->slots[s].state != kFree) return B200KV_EIO;
+  if (walked != n_free) return B200KV_EIO;
+  walked = 0;
+  uint32_t prev = kNone;
+  for (uint32_t s = pool->h->lru_head; s != kNone; prev = s, s = pool->slots[s].lru_next)
+    if (++walked > n || pool->slots[s].state != kReady || pool->slots[s].lru_prev != prev) return B200KV_EIO;
+  if (walked != n_ready || pool->h->lru_tail != prev) return B200KV_EIO;
+  return B200KV_OK;
+}
+
 extern "C" int b200kv_pool_clear(b200kv_pool* pool) {
   if (!pool) return B200KV_EINVAL;
-  b200kv_pool::Guard g(pool->h);
+  b200kv_pool::Guard g(pool);
   int busy = 0;
   for (uint32_t s = 0; s < pool->h->n_slots; ++s) {
     Slot& e = pool->slots[s];

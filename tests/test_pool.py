@@ -164,3 +164,105 @@ def test_bad_arguments():
         KVPool("no-leading-slash", 8192, 4096, _lib.POOL_CREATE)
     with pytest.raises(B200KVError):
         KVPool("/b200kv-does-not-exist", 0, 0, _lib.POOL_ATTACH)
+
+
+# ---- failure detection: processes that die mid-protocol ------------------------------------------
+def test_stale_writer_and_stale_pin_are_reclaimed(monkeypatch):
+    """A writer that died between reserve and commit, and a reader that died between acquire and
+    release, must not wedge the pool: both are recognised by age (B200KV_POOL_STALE_MS)."""
+    monkeypatch.setenv("B200KV_POOL_STALE_MS", "80")
+    p = mk(2)
+    p.reserve(1, 256)                      # never committed
+    put(p, 2)
+    p.acquire(2)                           # never released
+    for key in (1, 3):                     # young: the key is somebody's / nothing can be evicted
+        with pytest.raises(B200KVError) as ei:
+            p.reserve(key, 256)
+        assert ei.value.code == (_lib.EEXIST if key == 1 else _lib.ENOSPC)
+    time.sleep(0.15)
+    put(p, 1, fill=7)                      # the dead writer's key is taken over
+    put(p, 3)                              # the dead reader's pin no longer protects chunk 2
+    keys = np.array([2], np.uint64)
+    assert p.lookup(keys, np.array([256], np.int32))[0] == 0
+    st = p.stats()
+    assert st["n_reclaimed_chunks"] == 2 and st["n_used"] == 2 and p.check()
+    slot, _, _ = p.acquire(1)
+    assert int(p.slot_view(slot)[0]) == 7
+    p.release(1)
+    p.close()
+
+
+def _hammer(name, ready):
+    c = KVPool(name, 0, SLOT, _lib.POOL_ATTACH)
+    k = 10_000
+    while True:                            # killed from outside, possibly inside a critical section
+        k += 1
+        if k == 10_200:
+            ready.set()
+        try:
+            c.reserve(k, 256)
+            c.commit(k)
+            c.acquire(k)
+            c.release(k)
+        except B200KVError:
+            pass
+
+
+def test_pool_survives_a_process_killed_at_any_point(shm_name):
+    """SIGKILL a process that is reserving/committing/evicting in a tight loop, many times: whatever
+    it held must not break the others (b200kv_pool_check verifies lists and table)."""
+    import os
+    import signal
+    p = KVPool(shm_name, 8 * SLOT, SLOT, _lib.POOL_CREATE)
+    ctx = mp.get_context("spawn")
+    for round_ in range(4):
+        ready = ctx.Event()
+        proc = ctx.Process(target=_hammer, args=(shm_name, ready))
+        proc.start()
+        assert ready.wait(60)
+        time.sleep(0.003 * (round_ + 1))
+        os.kill(proc.pid, signal.SIGKILL)  # exactly the process started above
+        proc.join(30)
+        assert p.check(), f"round {round_}: inconsistent after kill"
+        put(p, 500 + round_, fill=round_)  # the pool still takes writes and serves them
+        slot, n, _ = p.acquire(500 + round_)
+        assert int(p.slot_view(slot)[0]) == round_
+        p.release(500 + round_)
+    assert p.stats()["n_used"] <= 8 and p.check()
+    p.close()
+
+
+def _die_in_reserve(name):
+    os_env_key = 777
+    c = KVPool(name, 0, SLOT, _lib.POOL_ATTACH)
+    put(c, 5, fill=5)
+    c.reserve(os_env_key, 256)             # B200KV_POOL_TEST_DIE_KEY=777: _exit(9) with the lock held
+
+
+def test_lock_owner_death_rebuilds_the_index(shm_name, monkeypatch):
+    """Deterministic version: the child exits INSIDE reserve's critical section (fault injection),
+    slot written and hashed but the counters not yet updated.  The next caller gets EOWNERDEAD,
+    rebuilds free list / LRU / table from the slot array, and carries on."""
+    p = KVPool(shm_name, 4 * SLOT, SLOT, _lib.POOL_CREATE)
+    put(p, 1, fill=1)
+    put(p, 2, fill=2)
+    monkeypatch.setenv("B200KV_POOL_TEST_DIE_KEY", "777")
+    ctx = mp.get_context("spawn")
+    proc = ctx.Process(target=_die_in_reserve, args=(shm_name,))
+    proc.start()
+    proc.join(60)
+    assert proc.exitcode == 9
+    monkeypatch.delenv("B200KV_POOL_TEST_DIE_KEY")
+    keys = np.array([1, 2, 5], np.uint64)
+    ct = np.array([256] * 3, np.int32)
+    assert p.lookup(keys, ct)[0] == 3      # first call after the death: recovers, then answers
+    st = p.stats()
+    assert st["n_recoveries"] == 1 and st["n_used"] == 4 and p.check()   # 1, 2, 5 READY + 777 WRITING
+    with pytest.raises(B200KVError) as ei:
+        p.reserve(777, 256)                # the dead writer's reservation is still young
+    assert ei.value.code == _lib.EEXIST
+    for k in (1, 2, 5):
+        slot, _, _ = p.acquire(k)
+        assert int(p.slot_view(slot)[0]) == k
+        p.release(k)
+    p.close()
