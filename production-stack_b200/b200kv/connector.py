@@ -142,6 +142,11 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                                          self.cfg.save_decode_cache, self.kv_role, async_load=self.cfg.async_load)
             if self.kv_role != "kv_producer":     # the scheduler fetches every TP rank's chunks of a prompt
                 self._remote = self._make_remote([self._key_seed(r) for r in range(self._world)])
+            if not self.cfg.pool_name:
+                # a per-engine segment dies with its engine (vLLM's engine ids are random: nobody would
+                # ever attach to it again); a named, shared one stays for the other replicas of the box
+                import atexit
+                atexit.register(KVPool.unlink, self._pool_name)
         logger.info("b200kv connector role=%s kv_role=%s pool=%s (%.1f GB, chunk %d, fmt %s)",
                     role.name, self.kv_role, self._pool_name, self.cfg.max_local_cpu_size_gb, self._chunk,
                     "fp8" if self.cfg.fmt else "raw")
@@ -337,6 +342,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         if self._pool is not None:
             self._pool.close()
             self._pool = None
+            if self._sched is not None and not self.cfg.pool_name:
+                KVPool.unlink(self._pool_name)    # mappings of the workers stay valid until they exit
 
     # ------------------------------------------------------------------ scheduler side
     @_traced
