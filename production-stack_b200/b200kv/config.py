@@ -37,6 +37,8 @@ class B200KVConfig:
     controller_pull_url: str | None = None   # LMCACHE_CONTROLLER_PULL_URL  (router side binds)
     controller_reply_url: str | None = None  # LMCACHE_CONTROLLER_REPLY_URL
     worker_heartbeat_s: float = 10.0      # LMCACHE_LMCACHE_WORKER_HEARTBEAT_TIME
+    advertise_ip: str | None = None       # B200KV_ADVERTISE_IP / LMCACHE_P2P_HOST: the address the router knows this
+                                          # engine by (default: the pod's outbound IP)
     pool_name: str | None = None          # B200KV_POOL_NAME: POSIX shm name; shared => config 3
     staging_mb: int = 4096                # B200KV_STAGING_MB: device staging ring (half for stores, half for loads;
                                           # a layer-wise load needs all its chunks resident: 2 GiB = 8K tokens of Llama-3-8B)
@@ -82,6 +84,7 @@ class B200KVConfig:
         c.controller_pull_url = e.get("LMCACHE_CONTROLLER_PULL_URL") or e.get("LMCACHE_CONTROLLER_URL")
         c.controller_reply_url = e.get("LMCACHE_CONTROLLER_REPLY_URL")
         c.worker_heartbeat_s = float(e.get("LMCACHE_LMCACHE_WORKER_HEARTBEAT_TIME", c.worker_heartbeat_s))
+        c.advertise_ip = e.get("B200KV_ADVERTISE_IP") or e.get("LMCACHE_P2P_HOST") or None
         c.pool_name = e.get("B200KV_POOL_NAME") or None
         c.staging_mb = int(e.get("B200KV_STAGING_MB", c.staging_mb))
         c.lookup_lease_ms = int(e.get("B200KV_LOOKUP_LEASE_MS", c.lookup_lease_ms))

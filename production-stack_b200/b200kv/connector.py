@@ -215,7 +215,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             self._controller = ControllerClient(
                 self.cfg.controller_pull_url, self.cfg.instance_id, self._pool_name, self._engine.key_seed,
                 self._chunk, owner_tag=owner_tag_of(self.cfg.instance_id) if self.cfg.pool_name else 0,
-                include_partial=not self._discard_partial, heartbeat_s=self.cfg.worker_heartbeat_s)
+                include_partial=not self._discard_partial, heartbeat_s=self.cfg.worker_heartbeat_s,
+                ip=self.cfg.advertise_ip)
         logger.info("b200kv registered %d layers, %d blocks, stride %d", len(tensors), nb, stride)
 
     def _metas(self) -> list[ReqMeta]:

@@ -35,15 +35,27 @@ def question(k: int) -> str:
     return f"Here's question #{k}: can you tell me a new long story with a happy ending?"
 
 
-async def one_request(session, base_url, model, messages, max_tokens, uid):
+def flatten(messages) -> str:
+    """Completions mode: the conversation as ONE prompt string, so that the
+    router's kv-aware lookup tokenises exactly what the engine will see (a chat request goes through
+    the engine's chat template and would not match, src/vllm_router/routers/routing_logic.py:332-428)."""
+    return "\n".join(m["content"] for m in messages)
+
+
+async def one_request(session, base_url, model, messages, max_tokens, uid, api="chat"):
     t0 = time.time()
     first = None
     first_chunk = None
     text = []
     usage = {}
-    body = {"model": model, "messages": messages, "temperature": 0, "stream": True, "max_tokens": max_tokens,
+    body = {"model": model, "temperature": 0, "stream": True, "max_tokens": max_tokens,
             "stream_options": {"include_usage": True}}
-    async with session.post(base_url + "/chat/completions", json=body, headers={"x-user-id": str(uid)}) as r:
+    if api == "completions":
+        body["prompt"] = flatten(messages)
+    else:
+        body["messages"] = messages
+    path = "/completions" if api == "completions" else "/chat/completions"
+    async with session.post(base_url + path, json=body, headers={"x-user-id": str(uid)}) as r:
         r.raise_for_status()
         async for raw in r.content:
             line = raw.decode().strip()
@@ -61,7 +73,7 @@ async def one_request(session, base_url, model, messages, max_tokens, uid):
             if first_chunk is None:
                 first_chunk = time.time()
             delta = ch[0].get("delta", {})
-            piece = delta.get("content") or delta.get("reasoning_content")
+            piece = delta.get("content") or delta.get("reasoning_content") or ch[0].get("text")
             if piece:
                 if first is None:
                     first = time.time()
@@ -87,7 +99,8 @@ async def user_session(session, args, uid, start_delay, rows):
             prompt = system_prompt(uid, args.shared_system_prompt, args.user_history_prompt) + prompt
         history.append({"role": "user", "content": prompt})
         try:
-            res = await one_request(session, args.base_url, args.model, history, args.answer_len, uid)
+            res = await one_request(session, args.base_url, args.model, history, args.answer_len, uid,
+                                    getattr(args, "api", "chat"))
         except Exception as e:  # a failed request is recorded, not fatal (the harness logs and goes on)
             rows.append({"user_id": uid, "question_id": k, "error": repr(e)})
             return
@@ -142,6 +155,7 @@ def main():
     ap.add_argument("--user-history-prompt", type=int, default=1536)
     ap.add_argument("--answer-len", type=int, default=64)
     ap.add_argument("--init-user-id", type=int, default=0)
+    ap.add_argument("--api", choices=["chat", "completions"], default="chat")
     ap.add_argument("--output", default=None, help="per-request rows as JSON lines")
     args = ap.parse_args()
     rows, summary = asyncio.run(run(args))

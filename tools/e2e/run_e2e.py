@@ -51,13 +51,13 @@ def connector_args(mode: str, cpu_gb: float):
     raise ValueError(mode)
 
 
-def wait_ready(port: int, proc: subprocess.Popen, timeout: float) -> bool:
+def wait_ready(port: int, proc: subprocess.Popen, timeout: float, host: str = "127.0.0.1") -> bool:
     t0 = time.time()
     while time.time() - t0 < timeout:
         if proc.poll() is not None:
             return False
         try:
-            with urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=2) as r:
+            with urllib.request.urlopen(f"http://{host}:{port}/health", timeout=2) as r:
                 if r.status == 200:
                     return True
         except Exception:

@@ -1,7 +1,7 @@
 """Multi-replica multi-round-QA behind the UNMODIFIED reference router (BASELINE.json configs[2],
 scaled to the GPUs given): N `vllm serve` replicas, one per GPU, every one with B200KVConnector and
 — in the `shared` modes — ONE pinned host pool for the whole box (`B200KV_POOL_NAME`), fronted by
-`python -m vllm_router.app --service-discovery static --routing-logic <roundrobin|session|prefixaware>`
+`python -m vllm_router.app --service-discovery static --routing-logic <roundrobin|session|prefixaware|kvaware>`
 (pattern: /root/reference/tests/e2e/stress-test.sh:183-190), driven by tools/e2e/mrqa_driver.py.
 
 The router is the reference's own code: imported from /root/reference/src where that exists (the
@@ -18,6 +18,12 @@ Modes:
              from the server into the local pinned pool, then loaded
 
     python tools/e2e/run_multi.py --replicas 2 --routing roundrobin --modes none,private,shared
+
+`--routing kvaware` (BASELINE.json configs[3]): the router imports `lmcache.v1.cache_controller` from this
+repo's compat tree, every replica registers with it (LMCACHE_ENABLE_CONTROLLER, LMCACHE_CONTROLLER_PULL_URL,
+tutorials/assets/values-17-kv-aware.yaml:47-51), replica i listens on 127.0.0.(i+1) because the router
+tells instances apart by IP (routing_logic.py:413-423), the model is served under its directory name so
+the router can load the tokenizer, and the driver uses /v1/completions.
 """
 from __future__ import annotations
 
@@ -75,9 +81,9 @@ def killpg(proc):
             pass
 
 
-def scrape(port: int, needles=("external", "b200kv", "lmcache")) -> dict:
+def scrape(port: int, needles=("external", "b200kv", "lmcache"), host: str = "127.0.0.1") -> dict:
     try:
-        with urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=5) as r:
+        with urllib.request.urlopen(f"http://{host}:{port}/metrics", timeout=5) as r:
             txt = r.read().decode()
     except Exception:
         return {}
@@ -88,7 +94,7 @@ def scrape(port: int, needles=("external", "b200kv", "lmcache")) -> dict:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--replicas", type=int, default=2)
-    ap.add_argument("--routing", default="roundrobin", choices=["roundrobin", "session", "prefixaware"])
+    ap.add_argument("--routing", default="roundrobin", choices=["roundrobin", "session", "prefixaware", "kvaware"])
     ap.add_argument("--modes", default="none,private,shared")
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--model-dir", default="/tmp/llama3-8b-synth")
@@ -105,6 +111,7 @@ def main():
                     help="all replicas on GPU 0 (functional check of cross-replica reuse on one GPU: started one "
                          "after the other, --gpu-mem-util split between them; timings are not per-replica numbers)")
     ap.add_argument("--extra", default="", help="extra vllm serve args, e.g. --extra=--enforce-eager")
+    ap.add_argument("--kv-aware-threshold", type=int, default=2000)
     ap.add_argument("--mock", action="store_true", help="orchestration dry run: tools/mock_backend.py instead of vllm (no GPU)")
     args = ap.parse_args()
     os.makedirs(args.log_dir, exist_ok=True)
@@ -113,6 +120,9 @@ def main():
                         "--max-len", str(max(args.max_model_len, 8192))], check=True, stdout=subprocess.DEVNULL)
     rpath = router_path()
     results = []
+    kvaware = args.routing == "kvaware"
+    model_name = args.model_dir if kvaware else MODEL       # the router's tokenizer is loaded from this name
+    hosts = [f"127.0.0.{i + 1}" if kvaware else "127.0.0.1" for i in range(args.replicas)]
     for mode in args.modes.split(","):
         procs, logs = [], []
         t_mode = time.time()
@@ -131,33 +141,43 @@ def main():
                 gb = args.cpu_gb * (args.replicas if mode.startswith("shared") else 1)
                 env, cargs = replica_env(mode, 0 if args.same_gpu else i, gb, f"{os.getpid()}-{mode}")
                 env["LMCACHE_LMCACHE_INSTANCE_ID"] = f"replica-{i}"
+                if kvaware and mode != "none":
+                    env.update(LMCACHE_ENABLE_CONTROLLER="True", LMCACHE_CONTROLLER_PULL_URL="127.0.0.1:9000",
+                               LMCACHE_LMCACHE_WORKER_HEARTBEAT_TIME="2", B200KV_ADVERTISE_IP=hosts[i])
                 util = args.gpu_mem_util / args.replicas if args.same_gpu else args.gpu_mem_util
                 cmd = [sys.executable, "-m", "vllm.entrypoints.openai.api_server", "--model", args.model_dir,
-                       "--served-model-name", MODEL, "--load-format", "dummy", "--dtype", "bfloat16",
+                       "--served-model-name", model_name, "--load-format", "dummy", "--dtype", "bfloat16",
                        "--max-model-len", str(args.max_model_len), "--no-enable-prefix-caching",
                        "--gpu-memory-utilization", str(util), "--port", str(port), "--seed", "0",
-                       "--host", "127.0.0.1"] + cargs + (args.extra.split() if args.extra else [])
+                       "--host", hosts[i]] + cargs + (args.extra.split() if args.extra else [])
                 if args.mock:
-                    cmd = [sys.executable, os.path.join(ROOT, "tools", "mock_backend.py"), "--port", str(port), "--model", MODEL]
+                    cmd = [sys.executable, os.path.join(ROOT, "tools", "mock_backend.py"), "--host", hosts[i],
+                           "--port", str(port), "--model", model_name]
                 log = open(os.path.join(args.log_dir, f"vllm_{mode}_{i}.log"), "w")
                 logs.append(log)
                 procs.append(subprocess.Popen(cmd, env=env, stdout=log, stderr=subprocess.STDOUT, start_new_session=True))
-                if args.same_gpu and not wait_ready(port, procs[-1], args.startup_timeout):
+                if args.same_gpu and not wait_ready(port, procs[-1], args.startup_timeout, hosts[i]):
                     break
             res["startup_s"] = time.time() - t_mode
             engines = procs[n_aux:]
-            if len(engines) != len(ports) or not all(wait_ready(p, pr, args.startup_timeout) for p, pr in zip(ports, engines)):
+            if len(engines) != len(ports) or not all(wait_ready(p, pr, args.startup_timeout, h) for p, pr, h in zip(ports, engines, hosts)):
                 res["error"] = "replicas not ready"
                 continue
             renv = dict(os.environ)
-            renv["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "stubs"), rpath, renv.get("PYTHONPATH", "")])
+            extra_path = [os.path.join(ROOT, "production-stack_b200", "compat"),
+                          os.path.join(ROOT, "production-stack_b200")] if kvaware else []
+            renv["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "stubs"), rpath, *extra_path,
+                                                  renv.get("PYTHONPATH", "")])
             renv["HF_HUB_OFFLINE"] = "1"
             rcmd = [sys.executable, "-m", "vllm_router.app", "--host", "127.0.0.1", "--port", "8090",
                     "--service-discovery", "static",
-                    "--static-backends", ",".join(f"http://127.0.0.1:{p}" for p in ports),
-                    "--static-models", ",".join([MODEL] * len(ports)), "--routing-logic", args.routing]
+                    "--static-backends", ",".join(f"http://{h}:{p}" for h, p in zip(hosts, ports)),
+                    "--static-models", ",".join([model_name] * len(ports)), "--routing-logic", args.routing]
             if args.routing == "session":
                 rcmd += ["--session-key", "x-user-id"]
+            if kvaware:
+                rcmd += ["--session-key", "x-user-id", "--lmcache-controller-port", "9000",
+                         "--kv-aware-threshold", str(args.kv_aware_threshold)]
             rlog = open(os.path.join(args.log_dir, f"router_{mode}.log"), "w")
             logs.append(rlog)
             router = subprocess.Popen(rcmd, env=renv, stdout=rlog, stderr=subprocess.STDOUT, start_new_session=True)
@@ -165,7 +185,8 @@ def main():
             if not wait_ready(8090, router, 120):
                 res["error"] = "router not ready"
                 continue
-            d = argparse.Namespace(base_url="http://127.0.0.1:8090/v1", model=MODEL, num_users=args.num_users,
+            d = argparse.Namespace(base_url="http://127.0.0.1:8090/v1", model=model_name, api="completions" if kvaware else "chat",
+                                   num_users=args.num_users,
                                    num_rounds=args.num_rounds, qps=args.qps,
                                    shared_system_prompt=args.shared_system_prompt,
                                    user_history_prompt=args.user_history_prompt, answer_len=args.answer_len,
@@ -179,7 +200,7 @@ def main():
             with open(os.path.join(args.log_dir, f"mrqa_rows_{mode}.jsonl"), "w") as f:
                 for r in rows:
                     f.write(json.dumps(r) + "\n")
-            res["replica_metrics"] = [scrape(p) for p in ports]
+            res["replica_metrics"] = [scrape(p, host=h) for p, h in zip(ports, hosts)]
             res["router_requests_per_backend"] = scrape(8090, ("vllm:num_incoming_requests", "current_qps", "num_requests"))
         finally:
             for p in reversed(procs):
