@@ -42,6 +42,31 @@ def flatten(messages) -> str:
     return "\n".join(m["content"] for m in messages)
 
 
+async def one_request_blocking(session, base_url, model, messages, max_tokens, uid, api="chat"):
+    """stream=False variant.  The reference router's orchestrated P/D path returns its StreamingResponse
+    from inside the `async with` that owns the decode connection
+    (src/vllm_router/services/request_service/request.py:846-872), so a streamed answer that has not fully
+    arrived yet is cut off; through that path only non-streamed requests are reliable.  TTFT is then not
+    observable at the client: `ttft` carries the total latency and the row says so."""
+    t0 = time.time()
+    body = {"model": model, "temperature": 0, "stream": False, "max_tokens": max_tokens}
+    if api == "completions":
+        body["prompt"] = flatten(messages)
+    else:
+        body["messages"] = messages
+    path = "/completions" if api == "completions" else "/chat/completions"
+    async with session.post(base_url + path, json=body, headers={"x-user-id": str(uid)}) as r:
+        r.raise_for_status()
+        obj = await r.json()
+    t1 = time.time()
+    ch = (obj.get("choices") or [{}])[0]
+    text = ch.get("text") if api == "completions" else (ch.get("message") or {}).get("content")
+    usage = obj.get("usage") or {}
+    return {"body": text or "", "ttft": t1 - t0, "ttft_is_total_latency": True, "generation_time": 0.0,
+            "prompt_tokens": usage.get("prompt_tokens", 0), "generation_tokens": usage.get("completion_tokens", 0),
+            "launch_time": t0, "finish_time": t1}
+
+
 async def one_request(session, base_url, model, messages, max_tokens, uid, api="chat"):
     t0 = time.time()
     first = None
@@ -99,8 +124,8 @@ async def user_session(session, args, uid, start_delay, rows):
             prompt = system_prompt(uid, args.shared_system_prompt, args.user_history_prompt) + prompt
         history.append({"role": "user", "content": prompt})
         try:
-            res = await one_request(session, args.base_url, args.model, history, args.answer_len, uid,
-                                    getattr(args, "api", "chat"))
+            fn = one_request if getattr(args, "stream", True) else one_request_blocking
+            res = await fn(session, args.base_url, args.model, history, args.answer_len, uid, getattr(args, "api", "chat"))
         except Exception as e:  # a failed request is recorded, not fatal (the harness logs and goes on)
             rows.append({"user_id": uid, "question_id": k, "error": repr(e)})
             return
@@ -156,6 +181,7 @@ def main():
     ap.add_argument("--answer-len", type=int, default=64)
     ap.add_argument("--init-user-id", type=int, default=0)
     ap.add_argument("--api", choices=["chat", "completions"], default="chat")
+    ap.add_argument("--no-stream", dest="stream", action="store_false", help="stream=False; ttft = total latency")
     ap.add_argument("--output", default=None, help="per-request rows as JSON lines")
     args = ap.parse_args()
     rows, summary = asyncio.run(run(args))

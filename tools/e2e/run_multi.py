@@ -24,6 +24,11 @@ repo's compat tree, every replica registers with it (LMCACHE_ENABLE_CONTROLLER, 
 tutorials/assets/values-17-kv-aware.yaml:47-51), replica i listens on 127.0.0.(i+1) because the router
 tells instances apart by IP (routing_logic.py:413-423), the model is served under its directory name so
 the router can load the tokenizer, and the driver uses /v1/completions.
+
+`--routing pd` (BASELINE.json configs[4]): `--routing-logic disaggregated_prefill_orchestrated`; the first
+half of the replicas are prefillers (label p), the rest decoders (label d)
+(examples/disaggregated_prefill_orchestrated/router-deploy.yaml:124-136); every turn is prefilled on a
+p replica and its KV pulled by a d replica over NVLink (b200kv/pd.py).  Needs one GPU per replica.
 """
 from __future__ import annotations
 
@@ -94,7 +99,7 @@ def scrape(port: int, needles=("external", "b200kv", "lmcache"), host: str = "12
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--replicas", type=int, default=2)
-    ap.add_argument("--routing", default="roundrobin", choices=["roundrobin", "session", "prefixaware", "kvaware"])
+    ap.add_argument("--routing", default="roundrobin", choices=["roundrobin", "session", "prefixaware", "kvaware", "pd"])
     ap.add_argument("--modes", default="none,private,shared")
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--model-dir", default="/tmp/llama3-8b-synth")
@@ -175,6 +180,11 @@ def main():
                     "--static-models", ",".join([model_name] * len(ports)), "--routing-logic", args.routing]
             if args.routing == "session":
                 rcmd += ["--session-key", "x-user-id"]
+            if args.routing == "pd":
+                n_p = max(1, args.replicas // 2)
+                rcmd[rcmd.index("--routing-logic") + 1] = "disaggregated_prefill_orchestrated"
+                rcmd += ["--static-model-labels", ",".join(["p"] * n_p + ["d"] * (args.replicas - n_p)),
+                         "--prefill-model-labels", "p", "--decode-model-labels", "d"]
             if kvaware:
                 rcmd += ["--session-key", "x-user-id", "--lmcache-controller-port", "9000",
                          "--kv-aware-threshold", str(args.kv_aware_threshold)]
@@ -186,6 +196,7 @@ def main():
                 res["error"] = "router not ready"
                 continue
             d = argparse.Namespace(base_url="http://127.0.0.1:8090/v1", model=model_name, api="completions" if kvaware else "chat",
+                                   stream=args.routing != "pd",   # see mrqa_driver.one_request_blocking
                                    num_users=args.num_users,
                                    num_rounds=args.num_rounds, qps=args.qps,
                                    shared_system_prompt=args.shared_system_prompt,
