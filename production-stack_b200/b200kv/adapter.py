@@ -114,7 +114,7 @@ def make_req_meta(tracker: RequestTracker, block_size: int, chunk: int, load_spe
                    token_ids=np.asarray(tracker.token_ids[:n_tok], dtype=np.int32),
                    block_ids=list(tracker.allocated_block_ids),
                    is_last_prefill=is_last_prefill,
-                   save_spec=SaveSpec(skip_leading, (not skip_save) and n_save > 0),
+                   save_spec=SaveSpec(skip_leading, not skip_save),   # can be a 0-token save, like the reference
                    load_spec=load_spec)
 
 
