@@ -28,7 +28,7 @@ class LMCacheConnectorV1Impl:
         return self._inner.start_load_kv(forward_context, **kwargs)
 
     def wait_for_layer_load(self, layer_name):
-        return None
+        return self._inner.wait_for_layer_load(layer_name)   # layer-wise loads are the default
 
     def save_kv_layer(self, layer_name, kv_layer, attn_metadata, **kwargs):
         return None

@@ -111,6 +111,51 @@ def test_lmcache_named_alias_resolves():
         sys.path.pop(0)
 
 
+def test_vllm_builtin_lmcache_wrapper_drives_this_engine(monkeypatch):
+    """The chart's literal `{"kv_connector":"LMCacheConnectorV1"}`: vLLM's own wrapper class
+    (lmcache_connector.py:72-354) imports `lmcache.integration.vllm.vllm_v1_adapter` — here the compat
+    tree — and forwards the scheduler calls to this engine."""
+    from vllm.config import KVTransferConfig
+    from vllm.distributed.kv_transfer.kv_connector.factory import KVConnectorFactory
+    from vllm.distributed.kv_transfer.kv_connector.v1.base import KVConnectorRole
+
+    from b200kv import KVPool, chunk_keys
+    from b200kv.connector import geometry_from_vllm
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "production-stack_b200", "compat"))
+    monkeypatch.setenv("LMCACHE_MAX_LOCAL_CPU_SIZE", "0.05")
+    monkeypatch.setenv("LMCACHE_CHUNK_SIZE", "64")
+    for mod in [m for m in sys.modules if m == "lmcache" or m.startswith("lmcache.")]:
+        monkeypatch.delitem(sys.modules, mod)
+    cfg = fake_vllm_config(f"w{os.getpid()}x{os.urandom(3).hex()}")
+    cfg.kv_transfer_config = KVTransferConfig(kv_connector="LMCacheConnectorV1", kv_role="kv_both",
+                                              engine_id=cfg.kv_transfer_config.engine_id)
+    cls = KVConnectorFactory.get_connector_class(cfg.kv_transfer_config)
+    assert cls.__name__ == "LMCacheConnectorV1" and cls.__module__.startswith("vllm.")
+    conn = cls(cfg, KVConnectorRole.SCHEDULER, None)
+    inner = conn._lmcache_engine._inner
+    try:
+        assert type(conn._lmcache_engine).__module__ == "lmcache.integration.vllm.vllm_v1_adapter"
+        prompt = list(range(200))
+        req = NS(request_id="r1", prompt_token_ids=prompt, num_tokens=200, all_token_ids=prompt)
+        assert conn.get_num_new_matched_tokens(req, 0) == (0, False)
+        geom = geometry_from_vllm(cfg, inner.cfg)
+        for k in chunk_keys(np.asarray(prompt, np.int32), 64, geom.key_seed("synth-llama", 1, 0))[:2]:
+            inner._pool.reserve(int(k), 64, 0, 0)
+            inner._pool.commit(int(k))
+        assert conn.get_num_new_matched_tokens(req, 0) == (128, False)
+        conn.update_state_after_alloc(req, None, 128)
+        so = NS(scheduled_new_reqs=[NS(req_id="r1", prompt_token_ids=prompt, block_ids=(list(range(13)),),
+                                       num_computed_tokens=128)],
+                scheduled_cached_reqs=NS(req_ids=[], new_block_ids=[], resumed_req_ids=set(), all_token_ids={}),
+                num_scheduled_tokens={"r1": 72}, finished_req_ids=set())
+        meta = conn.build_connector_meta(so)
+        assert meta.requests[0].load_spec.can_load and meta.requests[0].load_spec.external_cached_tokens == 128
+        assert conn.request_finished(req, []) == (False, None)
+    finally:
+        inner.shutdown()
+        KVPool.unlink(inner._pool_name)
+
+
 def test_lmcache_prometheus_series_names_and_aggregation():
     """The series production-stack's Grafana dashboard queries
     (/root/reference/helm/dashboards/lmcache-dashboard.json:204,295,389,453,517)."""
