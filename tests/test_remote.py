@@ -220,3 +220,36 @@ def test_lmcache_server_entry_point_and_probe(tmp_path):
     assert subprocess.run([sys.executable, "-m", "b200kv.server", "--probe", "127.0.0.1", str(port)],
                           env=dict(os.environ, PYTHONPATH=os.path.join(ROOT, "production-stack_b200")),
                           timeout=60, stderr=subprocess.DEVNULL).returncode == 1
+
+
+def test_server_aborts_half_received_put_and_rejects_garbage(server):
+    """A client that dies in the middle of an upload must not leave a half-written chunk behind, and a
+    peer speaking another protocol is dropped without harming the server."""
+    import socket
+    import struct
+    s = socket.create_connection(("127.0.0.1", server.port))
+    # header: magic, version, op=PUT(2), key, fmt, n_tokens, owner, status, length, slot_bytes  (48 bytes, LE)
+    hdr = struct.pack("<IHHQIiIiQQ", 0x564B3242, 1, 2, 4242, 0, 256, 0, 0, SLOT, SLOT)
+    assert len(hdr) == 48
+    s.sendall(hdr)
+    rep = s.recv(48, socket.MSG_WAITALL)
+    assert struct.unpack("<IHHQIiIiQQ", rep)[7] == 0          # "send it"
+    s.sendall(b"x" * (SLOT // 2))
+    s.close()                                                 # dies half way
+    g = socket.create_connection(("127.0.0.1", server.port))
+    g.sendall(b"GET / HTTP/1.1\r\nHost: x\r\n\r\n" + b"\0" * 32)
+    try:
+        assert g.recv(64) == b""                              # connection dropped (FIN) ...
+    except ConnectionResetError:
+        pass                                                  # ... or reset, because unread bytes were pending
+    g.close()
+    c = RemoteClient("127.0.0.1", server.port)
+    t0 = time.time()
+    while c.stats()["n_used"] != 0:                           # the reservation is aborted once the socket closes
+        assert time.time() - t0 < 5
+        time.sleep(0.01)
+    assert c.exists(np.array([4242], np.uint64)) == 0
+    a = mk_pool(2)
+    put_local(a, 4242, 256, 9)
+    assert c.put(a, 4242, 0) == 0                             # the key can be stored afterwards
+    c.close()
