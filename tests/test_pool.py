@@ -266,3 +266,29 @@ def test_lock_owner_death_rebuilds_the_index(shm_name, monkeypatch):
         assert int(p.slot_view(slot)[0]) == k
         p.release(k)
     p.close()
+
+
+def _store_and_exit(name):
+    c = KVPool(name, 4 * SLOT, SLOT, _lib.POOL_CREATE_OR_ATTACH)
+    put(c, 900, 256, fill=9)
+    put(c, 901, 77, fill=8)
+    # no close(), no unlink: the engine process just goes away
+
+
+def test_named_pool_survives_engine_restart(shm_name):
+    """Warm restart (SURVEY.md §5 checkpoint/resume, for this path): with B200KV_POOL_NAME the KV a
+    replica offloaded outlives the replica — a restarted engine attaches to the same segment and finds
+    its chunks, sized and tagged as they were."""
+    ctx = mp.get_context("spawn")
+    p1 = ctx.Process(target=_store_and_exit, args=(shm_name,))
+    p1.start()
+    p1.join(60)
+    assert p1.exitcode == 0
+    again = KVPool(shm_name, 4 * SLOT, SLOT, _lib.POOL_CREATE_OR_ATTACH)     # what the restarted connector does
+    assert again.lookup(np.array([900, 901], np.uint64), np.array([256, 77], np.int32)) == (2, 333)
+    slot, n, _ = again.acquire(901)
+    assert n == 77 and int(again.slot_view(slot)[0]) == 8
+    again.release(901)
+    with pytest.raises(B200KVError):                                          # another model geometry: refused
+        KVPool(shm_name, 4 * SLOT, 2 * SLOT, _lib.POOL_CREATE_OR_ATTACH)
+    again.close()
