@@ -130,8 +130,13 @@ class SchedulerState:
     """Scheduler-role half.  `lookup(token_ids) -> hit tokens` is injected (pool index)."""
 
     def __init__(self, lookup, block_size: int, chunk: int, discard_partial_chunks: bool,
-                 save_decode_cache: bool = False, kv_role: str = "kv_both", async_load: bool = False):
+                 save_decode_cache: bool = False, kv_role: str = "kv_both", async_load: bool = False,
+                 priority_limit: int | None = None):
         self.lookup = lookup
+        # requests whose priority value exceeds the limit are served from the cache but not saved
+        # (adapter :1163, :1332-1337: `request_priority > config.priority_limit`)
+        self.priority_limit = priority_limit
+        self._priority: dict[str, int] = {}
         # Asynchronous loads (KVConnectorBase_V1.get_num_new_matched_tokens -> (n, True)): the
         # request waits in WAITING_FOR_REMOTE_KVS while its KV streams in, other requests keep
         # running; vLLM itself recomputes the last token of a full hit
@@ -153,9 +158,10 @@ class SchedulerState:
 
     # get_num_new_matched_tokens (adapter :1141-1228); side-effect free apart from the lease
     def num_new_matched_tokens(self, req_id: str, prompt_token_ids, num_tokens: int,
-                               num_computed_tokens: int) -> int:
+                               num_computed_tokens: int, priority: int = 0) -> int:
         if self.kv_role == "kv_producer":
             return 0
+        self._priority[req_id] = priority
         hit = int(self.lookup(prompt_token_ids))
         self.num_lookups += 1
         self.num_hit_tokens += hit
@@ -193,14 +199,17 @@ class SchedulerState:
             self.unfinished.pop(rid, None)
             self.load_specs.pop(rid, None)
             self._async_saved.pop(rid, None)
+            self._priority.pop(rid, None)
         for req in scheduler_output.scheduled_new_reqs:
             spec = self.load_specs.pop(req.req_id, None)
             n_compute = req.num_computed_tokens + scheduler_output.num_scheduled_tokens[req.req_id]
             saved = spec.external_cached_tokens if spec is not None else self._async_saved.pop(req.req_id, 0)
             prompt = req.prompt_token_ids or []
+            prio = self._priority.pop(req.req_id, 0)
             tr = RequestTracker(req.req_id, len(prompt), list(prompt[:n_compute]),
                                 first_group(req.block_ids), num_saved_tokens=saved,
-                                skip_save=force_skip or request_skip_save(req))
+                                skip_save=force_skip or request_skip_save(req)
+                                or (self.priority_limit is not None and prio > self.priority_limit))
             self.trackers[req.req_id] = tr
             m = make_req_meta(tr, self.block_size, self.chunk, spec, self.discard_partial_chunks,
                               self.save_decode_cache)

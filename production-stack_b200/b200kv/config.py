@@ -32,6 +32,7 @@ class B200KVConfig:
     fmt: int = FMT_RAW                    # LMCACHE_REMOTE_SERDE=cachegen or B200KV_FORMAT=fp8 -> FMT_FP8
     save_unfull_chunk: bool = True        # LMCACHE_SAVE_UNFULL_CHUNK
     save_decode_cache: bool = False       # LMCACHE_SAVE_DECODE_CACHE
+    priority_limit: int | None = None     # LMCACHE_PRIORITY_LIMIT: requests with priority > limit are not saved
     instance_id: str = "b200kv_default_instance"   # LMCACHE_LMCACHE_INSTANCE_ID (pod name)
     enable_controller: bool = False       # LMCACHE_ENABLE_CONTROLLER
     controller_pull_url: str | None = None   # LMCACHE_CONTROLLER_PULL_URL  (router side binds)
@@ -79,6 +80,7 @@ class B200KVConfig:
         c.fmt = FMT_FP8 if fmt == "fp8" else FMT_RAW
         c.save_unfull_chunk = _b(e.get("LMCACHE_SAVE_UNFULL_CHUNK"), True)
         c.save_decode_cache = _b(e.get("LMCACHE_SAVE_DECODE_CACHE"), False)
+        c.priority_limit = int(e["LMCACHE_PRIORITY_LIMIT"]) if e.get("LMCACHE_PRIORITY_LIMIT") not in (None, "") else None
         c.instance_id = e.get("LMCACHE_LMCACHE_INSTANCE_ID", c.instance_id)
         c.enable_controller = _b(e.get("LMCACHE_ENABLE_CONTROLLER"), False)
         c.controller_pull_url = e.get("LMCACHE_CONTROLLER_PULL_URL") or e.get("LMCACHE_CONTROLLER_URL")

@@ -139,7 +139,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                 return pool.lookup_tokens(token_ids, chunk, seed, lease, include_partial)
 
             self._sched = SchedulerState(lookup, self._block_size, self._chunk, self._discard_partial,
-                                         self.cfg.save_decode_cache, self.kv_role, async_load=self.cfg.async_load)
+                                         self.cfg.save_decode_cache, self.kv_role, async_load=self.cfg.async_load,
+                                         priority_limit=self.cfg.priority_limit)
             if self.kv_role != "kv_producer":     # the scheduler fetches every TP rank's chunks of a prompt
                 self._remote = self._make_remote([self._key_seed(r) for r in range(self._world)])
             if not self.cfg.pool_name:
@@ -358,7 +359,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                 request.request_id, request.prompt_token_ids or []) == self._remote.PENDING:
             return None, False   # chunks are on their way from the cache server: ask again next step
         n = self._sched.num_new_matched_tokens(request.request_id, request.prompt_token_ids or [],
-                                               request.num_tokens, num_computed_tokens)
+                                               request.num_tokens, num_computed_tokens,
+                                               int(getattr(request, "priority", 0) or 0))
         return n, bool(self._sched.async_load and n > 0)
 
     @_traced

@@ -312,3 +312,19 @@ def test_on_stored_hook_gets_the_new_chunk_keys_only():
     sched.after_alloc(r2, 0)
     w2.save(sched.build_meta(sched_out([new_req("z", p2, list(range(20, 24)))], num_sched={"z": C})))
     assert eng.calls[-1] == ("store", C, 0)
+
+
+def test_priority_limit_serves_but_does_not_save_low_priority_requests():
+    """LMCACHE_PRIORITY_LIMIT (adapter :1163, :1332-1337): a request whose priority value exceeds the
+    limit may load from the pool but its KV is not stored."""
+    eng = OracleBackedEngine([np.zeros((2, 64, BS, 1, 8), np.uint16)])
+    sched = SchedulerState(lambda t: 0, BS, C, False, priority_limit=1)
+    w = WorkerState(eng, BS, C)
+    for rid, prio, stored in (("lo", 5, False), ("hi", 1, True), ("dflt", 0, True)):
+        prompt = list(range(100, 100 + 2 * C))
+        req = NS(request_id=rid, prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt)
+        sched.num_new_matched_tokens(rid, prompt, len(prompt), 0, priority=prio)
+        sched.after_alloc(req, 0)
+        n = len(eng.calls)
+        w.save(sched.build_meta(sched_out([new_req(rid, prompt, list(range(8)))], num_sched={rid: len(prompt)})))
+        assert (len(eng.calls) > n) == stored, rid
