@@ -97,3 +97,37 @@ def test_driver_sends_what_the_unmodified_harness_sends(tmp_path):
     assert len(common) >= 12, (sorted(a), sorted(b))         # several users, all three turns of most of them
     for k in common:
         assert a[k] == b[k], k
+
+
+def test_run_e2e_can_drive_with_the_unmodified_harness(tmp_path):
+    """`run_e2e.py --harness`: the engines are driven by the reference's own multi-round-qa.py (from the
+    reference tree here, from baseline/_ref on the GPU box) and p50 TTFT is computed from its CSV."""
+    import argparse
+    import socket
+    import time
+    import urllib.request
+    sys.path.insert(0, os.path.join(ROOT, "tools", "e2e"))
+    import run_e2e
+    if run_e2e.harness_path() is None:
+        pytest.skip("reference harness not present on this machine")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mock = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "mock_backend.py"), "--port", str(port), "--model", "m"],
+                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, start_new_session=True)
+    try:
+        for _ in range(100):
+            try:
+                urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=1)
+                break
+            except Exception:
+                time.sleep(0.2)
+        a = argparse.Namespace(num_users=3, num_rounds=2, qps=3.0, shared_system_prompt=20, user_history_prompt=20, answer_len=6)
+        res = run_e2e.run_harness(f"http://127.0.0.1:{port}/v1", "m", a, str(tmp_path / "h.csv"), 6)
+        assert res["harness_exit"] == 0 and res["requests"] >= 6, res
+        assert res["ttft_p50_s"] is not None and res["ttft_p50_s"] < 1.0 and res["output_tokens_per_s"] > 0
+        assert "multi-round-qa.py" in res["driver"]
+    finally:
+        mock.terminate()                  # exactly the process started above
+        mock.wait(20)
