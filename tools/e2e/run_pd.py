@@ -78,31 +78,29 @@ async def drive(args, p_urls, d_urls):
 
 
 async def one_request(args, s, i, p_url, d_url):
-    if True:
-        if True:
-            prompt = f"request {i} " + " ".join(["hi"] * args.prompt_words)
-            base = {"model": "synth-llama3-8b", "prompt": prompt, "max_tokens": args.max_tokens, "temperature": 0}
-            # reference: one engine does everything (decode engine, no hand-off)
-            ref_ttft, ref_text = await stream_completion(s, d_url + "/v1/completions", dict(base, stream=True))
-            # step 1: prefill
-            t0 = time.time()
-            pre = dict(base, max_tokens=1, stream=False,
-                       kv_transfer_params={"do_remote_decode": True, "do_remote_prefill": False, "remote_engine_id": None,
-                                           "remote_block_ids": None, "remote_host": None, "remote_port": None})
-            async with s.post(p_url + "/v1/completions", json=pre) as r:
-                r.raise_for_status()
-                pdata = await r.json()
-            t_prefill = time.time() - t0
-            ktp = pdata.get("kv_transfer_params") or {}
-            if ktp:
-                ktp["remote_host"] = "127.0.0.1"
-            # step 2: decode with the hand-off
-            d_ttft, d_text = await stream_completion(s, d_url + "/v1/completions",
-                                                     dict(base, stream=True, kv_transfer_params=ktp))
-            return {"prefill_s": t_prefill, "decode_ttft_s": d_ttft, "single_engine_ttft_s": ref_ttft,
-                    "handoff_params": bool(ktp), "n_remote_blocks": len((ktp.get("remote_block_ids") or [])),
-                    "same_text": hashlib.sha1(d_text.encode()).hexdigest() == hashlib.sha1(ref_text.encode()).hexdigest(),
-                    "prompt_tokens": pdata.get("usage", {}).get("prompt_tokens"), "prefill": p_url, "decode": d_url}
+    prompt = f"request {i} " + " ".join(["hi"] * args.prompt_words)
+    base = {"model": "synth-llama3-8b", "prompt": prompt, "max_tokens": args.max_tokens, "temperature": 0}
+    # reference: one engine does everything (decode engine, no hand-off)
+    ref_ttft, ref_text = await stream_completion(s, d_url + "/v1/completions", dict(base, stream=True))
+    # step 1: prefill
+    t0 = time.time()
+    pre = dict(base, max_tokens=1, stream=False,
+               kv_transfer_params={"do_remote_decode": True, "do_remote_prefill": False, "remote_engine_id": None,
+                                   "remote_block_ids": None, "remote_host": None, "remote_port": None})
+    async with s.post(p_url + "/v1/completions", json=pre) as r:
+        r.raise_for_status()
+        pdata = await r.json()
+    t_prefill = time.time() - t0
+    ktp = pdata.get("kv_transfer_params") or {}
+    if ktp:
+        ktp["remote_host"] = "127.0.0.1"
+    # step 2: decode with the hand-off
+    d_ttft, d_text = await stream_completion(s, d_url + "/v1/completions",
+                                             dict(base, stream=True, kv_transfer_params=ktp))
+    return {"prefill_s": t_prefill, "decode_ttft_s": d_ttft, "single_engine_ttft_s": ref_ttft,
+            "handoff_params": bool(ktp), "n_remote_blocks": len((ktp.get("remote_block_ids") or [])),
+            "same_text": hashlib.sha1(d_text.encode()).hexdigest() == hashlib.sha1(ref_text.encode()).hexdigest(),
+            "prompt_tokens": pdata.get("usage", {}).get("prompt_tokens"), "prefill": p_url, "decode": d_url}
 
 
 def metrics_of(port):
