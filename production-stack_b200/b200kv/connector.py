@@ -396,6 +396,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         # Offload: the gather that reads a request's pages is ordered before any later forward pass
         # on the compute stream, so blocks may be freed immediately.  Disaggregated prefill: keep
         # the pages (delay_free) until the decoder has pulled them (b200kv/pd.py).
+        self._remote_computed.pop(request.request_id, None)   # looked up as a remote prefill but never allocated
         if self._remote is not None:
             self._remote.forget(request.request_id)
         if self._pd is not None:
