@@ -197,6 +197,7 @@ struct b200kv_ctx {
   // bulk-kernel launch shape
   int S = 2, LAG = 1, ctas_per_sm = 1;  // swept on B200: profiles/sweep_r01.txt
   int fp8_threads = 256;                // B200KV_FP8_THREADS: CTA width of the FP8 store kernel
+  bool fp8_two_pass = false;            // B200KV_FP8_2PASS=1: smem-free two-pass store kernel (experimental)
   uint32_t piece_tokens = 0, pieces = 0, stage_bytes = 0;
 };
 
@@ -489,7 +490,8 @@ int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView&
     CU_TRY(cudaFuncSetAttribute(kv_fp8_store_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev] = true;
   }
-  if (ctx->fp8_threads == 512) kv_fp8_store_kernel<512><<<grid, 512, smem, s>>>(p);
+  if (ctx->fp8_two_pass && ctx->g.C / kCluster <= static_cast<uint32_t>(kMaxWindow)) kv_fp8_store2_kernel<<<grid, 256, 0, s>>>(p);
+  else if (ctx->fp8_threads == 512) kv_fp8_store_kernel<512><<<grid, 512, smem, s>>>(p);
   else kv_fp8_store_kernel<256><<<grid, 256, smem, s>>>(p);
   CU_TRY(cudaGetLastError());
   ++ctx->stats.n_kernel_launches;
@@ -680,6 +682,7 @@ static int engine_create_impl(const b200kv_engine_config* cfg, b200kv_pool* pool
   ctx->LAG = env_int("B200KV_LAG", ctx->S / 2);
   ctx->ctas_per_sm = cfg->ctas_per_sm > 0 ? cfg->ctas_per_sm : env_int("B200KV_CTAS_PER_SM", 1);
   ctx->fp8_threads = env_int("B200KV_FP8_THREADS", 256) == 512 ? 512 : 256;
+  ctx->fp8_two_pass = env_int("B200KV_FP8_2PASS", 0) != 0;
   const uint32_t stage_max = static_cast<uint32_t>(env_int("B200KV_STAGE_KB", 32)) << 10;
   if (g.token_bytes > stage_max || stage_max > kStageMax * 2) return B200KV_ENOTSUP;
   ctx->piece_tokens = std::min<uint32_t>(g.bs, stage_max / g.token_bytes);
