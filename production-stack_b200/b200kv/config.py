@@ -50,6 +50,7 @@ class B200KVConfig:
     layerwise: bool = True                # B200KV_LAYERWISE / LMCACHE_USE_LAYERWISE: per-layer-group loads (default on:
                                           # TTFT 24.4 -> 19.3 ms, outputs identical; profiles/e2e_mrqa_r01.json)
     layer_group: int = 4                  # B200KV_LAYER_GROUP: layers per group
+    device_tier_gb: float = 0.0           # B200KV_DEVICE_TIER_GB: HBM kept as a chunk cache peers can pull from (0 = off)
     remote_url: str | None = None         # LMCACHE_REMOTE_URL=lm://host:port: cache-server tier (b200kv/remote.py)
     remote_wait_ms: int = 2000            # B200KV_REMOTE_WAIT_MS: longest a request waits for its remote prefetch
     extra: dict = field(default_factory=dict)
@@ -94,6 +95,7 @@ class B200KVConfig:
         c.async_load = _b(e.get("B200KV_ASYNC_LOAD"), False)
         c.layerwise = _b(e.get("B200KV_LAYERWISE", e.get("LMCACHE_USE_LAYERWISE")), True)
         c.layer_group = max(1, int(e.get("B200KV_LAYER_GROUP", c.layer_group)))
+        c.device_tier_gb = float(e.get("B200KV_DEVICE_TIER_GB", c.device_tier_gb))
         c.remote_url = e.get("LMCACHE_REMOTE_URL") or None
         c.remote_wait_ms = int(e.get("B200KV_REMOTE_WAIT_MS", c.remote_wait_ms))
         for k in _IGNORED:

@@ -135,8 +135,23 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             pool = self._pool
             include_partial = not self._discard_partial
 
+            self._tiers = None
+            if self.cfg.device_tier_gb > 0:      # index-only view of every replica's device tier
+                from .device_tier import TierSet
+                self._tiers = TierSet(self._engine_id, geom.chunk_bytes, None)
+            tiers = self._tiers
+
             def lookup(token_ids):
-                return pool.lookup_tokens(token_ids, chunk, seed, lease, include_partial)
+                if tiers is None:
+                    return pool.lookup_tokens(token_ids, chunk, seed, lease, include_partial)
+                from .device_tier import combined_prefix_tokens
+                from .engine import chunk_keys
+                import numpy as np
+                toks = np.asarray(token_ids, dtype=np.int32)
+                keys = chunk_keys(toks, chunk, seed, include_partial)
+                ct = np.minimum(chunk, len(toks) - np.arange(len(keys)) * chunk).astype(np.int32)
+                tiers.refresh()
+                return combined_prefix_tokens(pool, tiers, keys, ct, lease)
 
             self._sched = SchedulerState(lookup, self._block_size, self._chunk, self._discard_partial,
                                          self.cfg.save_decode_cache, self.kv_role, async_load=self.cfg.async_load,
@@ -202,6 +217,20 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._layer_hooks_seen = 0
         self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role,
                                    owner_tag=owner_tag_of(self.cfg.instance_id) if self.cfg.pool_name else 0)
+        if self.cfg.device_tier_gb > 0:
+            from .device_tier import LocalTier, TierSet
+            fmt_tag = self.cfg.fmt | (tile_layout << 8)
+            try:
+                n_slots = max(1, int(self.cfg.device_tier_gb * (1 << 30)) // geom.chunk_bytes)
+                self._worker.tiers = TierSet(self._engine_id, geom.chunk_bytes, fmt_tag, importer=self._engine.tier_import)
+                if self.kv_role != "kv_consumer":
+                    self._worker.local_tier = LocalTier(self._engine, self._engine_id, n_slots, t0.device.index or 0,
+                                                        fmt_tag, owner_tag_of(self.cfg.instance_id))
+                    self._worker.tiers.add_local(self._worker.local_tier)
+                logger.info("b200kv device tier: %d chunk slots in HBM", n_slots)
+            except Exception as e:
+                logger.warning("b200kv: device tier unavailable (%s)", e)
+                self._worker.tiers = self._worker.local_tier = None
         if self.kv_role != "kv_consumer":
             self._remote = self._make_remote(self._engine.key_seed)
             if self._remote is not None:
@@ -337,6 +366,14 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         if self._pdw is not None:
             unpublish_ipc(self._engine_id)
             self._pdw = None
+        if self._worker is not None and self._worker.tiers is not None:
+            if self._worker.local_tier is not None:
+                self._worker.local_tier.close()
+            self._worker.tiers.close()
+            self._worker.tiers = self._worker.local_tier = None
+        if getattr(self, "_tiers", None) is not None:
+            self._tiers.close()
+            self._tiers = None
         if self._engine is not None:
             self._engine.wait_all()
             self._engine.close()

@@ -199,6 +199,10 @@ struct b200kv_ctx {
   int fp8_threads = 256;                // B200KV_FP8_THREADS: CTA width of the FP8 store kernel
   bool fp8_two_pass = false;            // B200KV_FP8_2PASS=1: smem-free two-pass store kernel (experimental)
   uint32_t piece_tokens = 0, pieces = 0, stage_bytes = 0;
+
+  void* tier_base = nullptr;            // device chunk tier (b200kv_tier_create)
+  uint32_t tier_slots = 0;
+  std::vector<void*> tier_imports;      // peers' tiers opened over CUDA IPC
 };
 
 namespace {
@@ -773,6 +777,8 @@ extern "C" int b200kv_engine_destroy(b200kv_ctx* ctx) {
       cudaEventDestroy(e.second);
     }
   if (ctx->d_staging) cudaFree(ctx->d_staging);
+  for (void* m : ctx->tier_imports) cudaIpcCloseMemHandle(m);
+  if (ctx->tier_base) cudaFree(ctx->tier_base);
   if (ctx->d_bases) cudaFree(ctx->d_bases);
   for (cudaStream_t s : {ctx->s_gather, ctx->s_d2h, ctx->s_h2d, ctx->s_scatter})
     if (s) cudaStreamDestroy(s);
@@ -804,10 +810,15 @@ extern "C" int b200kv_register_kv(b200kv_ctx* ctx, const void* const* k_ptrs,
 // device-resident gather / scatter
 // ------------------------------------------------------------------------------------------------
 static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_tokens, void* dev_chunks,
-                          void* stream, bool is_gather) {
-  if (!ctx || !slots || n_tokens <= 0 || !dev_chunks) return B200KV_EINVAL;
+                          void* stream, bool is_gather, const uint64_t* chunk_ptrs = nullptr) {
+  if (!ctx || !slots || n_tokens <= 0 || (!dev_chunks && !chunk_ptrs)) return B200KV_EINVAL;
   if (!ctx->kv_registered) return B200KV_EINVAL;
   if (reinterpret_cast<uint64_t>(dev_chunks) % 16) return B200KV_EINVAL;
+  if (chunk_ptrs) {
+    const int64_t n = (n_tokens + ctx->g.C - 1) / ctx->g.C;
+    for (int64_t c = 0; c < n; ++c)
+      if (!chunk_ptrs[c] || chunk_ptrs[c] % 16) return B200KV_EINVAL;
+  }
   DeviceGuard dg(ctx->cfg.device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   const Geometry& g = ctx->g;
@@ -828,7 +839,8 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   uint32_t* offs = reinterpret_cast<uint32_t*>(tv.slot->host + tv.offs_off);
   size_t r = 0;
   for (uint32_t c = 0; c < n_chunks; ++c) {
-    addrs[c] = reinterpret_cast<uint64_t>(dev_chunks) + static_cast<uint64_t>(c) * g.chunk_bytes;
+    addrs[c] = chunk_ptrs ? chunk_ptrs[c]
+                          : reinterpret_cast<uint64_t>(dev_chunks) + static_cast<uint64_t>(c) * g.chunk_bytes;
     offs[c] = static_cast<uint32_t>(r);
     while (r < runs.size() && static_cast<uint32_t>(runs[r].b) / g.C == c) ++r;
   }
@@ -863,6 +875,58 @@ extern "C" int b200kv_gather(b200kv_ctx* ctx, const int64_t* slot_mapping, int64
 extern "C" int b200kv_scatter(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
                               const void* dev_chunks, void* stream) {
   return gather_scatter(ctx, slot_mapping, n_tokens, const_cast<void*>(dev_chunks), stream, false);
+}
+
+extern "C" int b200kv_gather_chunks(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                                    const uint64_t* chunk_ptrs, void* stream) {
+  return gather_scatter(ctx, slot_mapping, n_tokens, nullptr, stream, true, chunk_ptrs);
+}
+
+extern "C" int b200kv_scatter_chunks(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                                     const uint64_t* chunk_ptrs, void* stream) {
+  return gather_scatter(ctx, slot_mapping, n_tokens, nullptr, stream, false, chunk_ptrs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device chunk tier: a buffer of chunk-format slots in HBM, exported to peer replicas over CUDA IPC.
+// The index (which key sits in which slot, LRU, pins) is a b200kv_pool in shm owned by the host side.
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200kv_tier_create(b200kv_ctx* ctx, uint32_t n_slots, uint64_t* base_out) {
+  if (!ctx || !n_slots || !base_out) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->tier_base) return B200KV_EEXIST;
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, static_cast<size_t>(n_slots) * ctx->g.chunk_bytes));
+  ctx->tier_base = p;
+  ctx->tier_slots = n_slots;
+  *base_out = reinterpret_cast<uint64_t>(p);
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_tier_export(b200kv_ctx* ctx, b200kv_ipc_desc* desc_out) {
+  if (!ctx || !desc_out || !ctx->tier_base) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::memset(desc_out, 0, sizeof(*desc_out));
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, ctx->tier_base));
+  std::memcpy(desc_out->handle, &h, 64);
+  desc_out->offset = 0;
+  desc_out->alloc_bytes = static_cast<uint64_t>(ctx->tier_slots) * ctx->g.chunk_bytes;
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_tier_import(b200kv_ctx* ctx, const b200kv_ipc_desc* desc, uint64_t* mapped_base_out) {
+  if (!ctx || !desc || !mapped_base_out) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, desc->handle, 64);
+  void* base = nullptr;
+  CU_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->tier_imports.push_back(base);
+  *mapped_base_out = reinterpret_cast<uint64_t>(base) + desc->offset;
+  return B200KV_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
