@@ -332,6 +332,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         cur = {"num_stored_tokens": ws.num_stored_tokens, "num_loaded_tokens": ws.num_loaded_tokens,
                "retrieve_seconds": ws.retrieve_seconds, "retrieve_calls": ws.retrieve_calls,
                "load_shortfalls": ws.num_load_shortfalls, "num_foreign_loaded_tokens": ws.num_foreign_loaded_tokens,
+               "num_tier_local_tokens": ws.num_tier_local_tokens, "num_tier_peer_tokens": ws.num_tier_peer_tokens,
                # the scheduler's counters are per engine, not per TP rank: rank 0 reports them
                "num_hit_tokens": self._sched_counters[1] if getattr(self, "_rank", 0) == 0 else 0,
                "num_requested_tokens": self._sched_counters[2] if getattr(self, "_rank", 0) == 0 else 0,
