@@ -88,11 +88,14 @@ def owner_tag_of(instance_id: str) -> int:
     return (xxh64(instance_id.encode(), 0) & 0x7FFFFFFF) or 1
 
 
-def pool_name_for(vllm_config, cfg: B200KVConfig) -> str:
+def pool_name_for(vllm_config, cfg: B200KVConfig, chunk_bytes: int = 0) -> str:
     """One segment per engine unless B200KV_POOL_NAME names a shared one (BASELINE.json
-    config 3: "shared pinned-host KV pool" across the replicas of a box)."""
+    config 3: "shared pinned-host KV pool" across the replicas of a box).  A shared name is
+    suffixed with the chunk size: replicas of DIFFERENT models on one box (the chart's modelSpec is
+    a list) given the same name get one segment per geometry instead of failing to attach."""
     if cfg.pool_name:
-        return cfg.pool_name if cfg.pool_name.startswith("/") else "/" + cfg.pool_name
+        base = cfg.pool_name if cfg.pool_name.startswith("/") else "/" + cfg.pool_name
+        return f"{base}-{chunk_bytes:x}" if chunk_bytes else base
     eid = vllm_config.kv_transfer_config.engine_id or "engine"
     return "/b200kv-" + "".join(ch for ch in str(eid) if ch.isalnum() or ch in "-_")[:48]
 
@@ -114,7 +117,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         pc = vllm_config.parallel_config
         self._model = str(vllm_config.model_config.model)
         self._world = pc.tensor_parallel_size
-        self._pool_name = pool_name_for(vllm_config, self.cfg)
+        self._pool_name = pool_name_for(vllm_config, self.cfg, geom.chunk_bytes)
         self._pool = KVPool(self._pool_name, self.cfg.pool_bytes, geom.chunk_bytes, _lib.POOL_CREATE_OR_ATTACH)
         self._engine: KVEngine | None = None
         self._worker: WorkerState | None = None

@@ -147,25 +147,47 @@ struct b200kv_server {
   int port = 0;
   uint64_t pool_bytes = 0;
   std::mutex mu;               // guards pool creation, conns
-  b200kv_pool* pool = nullptr; // created by the first PUT (its slot size is the clients')
+  // One pool per chunk geometry, created by the first PUT of that slot size: the chart runs ONE cache
+  // server for every model it deploys (modelSpec is a list), and chunk sizes differ between models.
+  std::vector<std::pair<uint64_t, b200kv_pool*>> pools;
   std::set<int> conns;
   std::atomic<bool> stopping{false};
   std::atomic<int> live_threads{0};
   std::thread acceptor;
   std::atomic<uint64_t> n_put{0}, n_get{0}, n_get_miss{0}, bytes_in{0}, bytes_out{0};
 
+  // the pool of this slot size (created on demand), or nullptr
   b200kv_pool* pool_for(uint64_t slot_bytes) {
+    if (!slot_bytes || slot_bytes % 16) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    if (!pool && slot_bytes) {
-      b200kv_pool_config pc;
-      memset(&pc, 0, sizeof(pc));
-      pc.shm_name = nullptr;
-      pc.pool_bytes = pool_bytes < slot_bytes ? slot_bytes : pool_bytes;
-      pc.slot_bytes = slot_bytes;
-      pc.flags = B200KV_POOL_CREATE;
-      if (b200kv_pool_open(&pc, &pool) != B200KV_OK) pool = nullptr;
+    for (auto& p : pools)
+      if (p.first == slot_bytes) return p.second;
+    if (pools.size() >= 16) return nullptr;
+    b200kv_pool_config pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.shm_name = nullptr;
+    pc.pool_bytes = pool_bytes < slot_bytes ? slot_bytes : pool_bytes;
+    pc.slot_bytes = slot_bytes;
+    pc.flags = B200KV_POOL_CREATE;
+    b200kv_pool* np = nullptr;
+    if (b200kv_pool_open(&pc, &np) != B200KV_OK) return nullptr;
+    pools.emplace_back(slot_bytes, np);
+    return np;
+  }
+  std::vector<b200kv_pool*> all_pools() {
+    std::lock_guard<std::mutex> lk(mu);
+    std::vector<b200kv_pool*> v;
+    for (auto& p : pools) v.push_back(p.second);
+    return v;
+  }
+  // keys are namespaced by model and format, so a key lives in at most one pool
+  b200kv_pool* pool_holding(uint64_t key) {
+    for (b200kv_pool* p : all_pools()) {
+      int32_t hit = 0;
+      uint32_t owner = 0;
+      if (b200kv_pool_lookup_owner(p, &key, 1, &hit, &owner) == B200KV_OK && hit == 1) return p;
     }
-    return pool;
+    return nullptr;
   }
 
   void serve(int fd) {
@@ -183,8 +205,8 @@ struct b200kv_server {
           std::vector<uint64_t> keys(in.length / 8);
           if (in.length && !recv_all(fd, keys.data(), in.length)) return;
           int32_t hit = 0;
-          b200kv_pool* p = pool_for(0);
-          if (p && !keys.empty()) {
+          b200kv_pool* p = keys.empty() ? nullptr : pool_holding(keys[0]);
+          if (p) {
             std::vector<uint32_t> owners(keys.size());
             b200kv_pool_lookup_owner(p, keys.data(), static_cast<int32_t>(keys.size()), &hit, owners.data());
           }
@@ -194,7 +216,7 @@ struct b200kv_server {
         }
         case kGet: {
           if (in.length && !drain(fd, in.length)) return;
-          b200kv_pool* p = pool_for(0);
+          b200kv_pool* p = pool_holding(in.key);
           uint32_t slot = 0, fmt = 0;
           int32_t n_tok = 0;
           if (!p || b200kv_pool_acquire(p, in.key, &slot, &n_tok, &fmt) != B200KV_OK) {
@@ -217,7 +239,7 @@ struct b200kv_server {
           b200kv_pool* p = pool_for(in.slot_bytes);
           uint32_t slot = 0;
           int rc = B200KV_EINVAL;
-          if (p && in.length == in.slot_bytes && slot_bytes_of(p) == in.slot_bytes && in.n_tokens > 0)
+          if (p && in.length == in.slot_bytes && in.n_tokens > 0)
             rc = b200kv_pool_reserve(p, in.key, in.n_tokens, in.fmt, in.owner, &slot);
           out.status = rc;
           if (!send_all(fd, &out, sizeof(out))) {
@@ -237,10 +259,20 @@ struct b200kv_server {
         }
         case kStats: {
           if (in.length && !drain(fd, in.length)) return;
-          b200kv_pool_stats st;
+          b200kv_pool_stats st;   // summed over the pools; slot_bytes = the requester's geometry, if given
           memset(&st, 0, sizeof(st));
-          b200kv_pool* p = pool_for(0);
-          if (p) b200kv_pool_get_stats(p, &st);
+          for (b200kv_pool* p : all_pools()) {
+            b200kv_pool_stats one;
+            if (b200kv_pool_get_stats(p, &one) != B200KV_OK) continue;
+            if (in.slot_bytes && one.slot_bytes != in.slot_bytes) continue;
+            st.n_slots += one.n_slots;
+            st.n_used += one.n_used;
+            st.slot_bytes = one.slot_bytes;
+            st.n_lookups += one.n_lookups;
+            st.n_stored_chunks += one.n_stored_chunks;
+            st.n_evicted_chunks += one.n_evicted_chunks;
+            st.n_dropped_chunks += one.n_dropped_chunks;
+          }
           out.length = sizeof(st);
           if (!send_all(fd, &out, sizeof(out)) || !send_all(fd, &st, sizeof(st))) return;
           break;
@@ -349,7 +381,7 @@ extern "C" int b200kv_server_stop(b200kv_server* s) {
   ::close(s->wake_pipe[0]);
   ::close(s->wake_pipe[1]);
   if (s->live_threads.load() == 0) {
-    if (s->pool) b200kv_pool_close(s->pool);
+    for (auto& p : s->pools) b200kv_pool_close(p.second);
     delete s;
   }  // else: a connection thread is stuck in the kernel; leak the object rather than free it under the thread
   return B200KV_OK;

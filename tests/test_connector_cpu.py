@@ -257,3 +257,13 @@ def test_scheduler_waits_for_remote_prefetch_then_hits(monkeypatch):
         conn.shutdown()
         KVPool.unlink(conn._pool_name)
         srv.stop()
+
+
+def test_shared_pool_name_is_per_geometry(monkeypatch):
+    """Two models on one box with the same B200KV_POOL_NAME: one segment per chunk geometry."""
+    from b200kv.config import B200KVConfig
+    from b200kv.connector import pool_name_for
+    cfg = B200KVConfig(pool_name="box")
+    assert pool_name_for(None, cfg, 0x2000000) == "/box-2000000"
+    assert pool_name_for(None, cfg, 0x1000800) == "/box-1000800"
+    assert pool_name_for(NS(kv_transfer_config=NS(engine_id="e-1/x")), B200KVConfig(), 123) == "/b200kv-e-1x"

@@ -81,7 +81,7 @@ def test_put_get_roundtrip_is_bit_exact(server):
     c.close()
 
 
-def test_server_evicts_lru_and_reports_slot_mismatch(server):
+def test_server_evicts_lru_and_keeps_one_pool_per_geometry(server):
     a = mk_pool(16)
     c = RemoteClient("127.0.0.1", server.port)
     for k in range(1, 9):                                   # server holds 6 slots
@@ -89,11 +89,22 @@ def test_server_evicts_lru_and_reports_slot_mismatch(server):
         assert c.put(a, k, 0) == 0
     assert c.stats()["n_used"] == 6 and c.stats()["n_evicted_chunks"] == 2
     assert c.exists(np.array([1], np.uint64)) == 0 and c.exists(np.array([8, 7, 3], np.uint64)) == 3
-    other = KVPool(None, 4 * 2 * SLOT, 2 * SLOT, _lib.POOL_CREATE)     # a client with another geometry
+    # a second model on the same server (the chart deploys ONE cache server for all modelSpecs): its chunks
+    # have another size and live in a pool of their own, with their own LRU
+    other = KVPool(None, 4 * 2 * SLOT, 2 * SLOT, _lib.POOL_CREATE)
     slot = other.reserve(77, 256, 0, 0)
+    other.slot_view(slot)[:] = 5
     other.commit(77)
-    assert c.put(other, 77, 0) == _lib.EINVAL
-    assert c.get(other, 8, 0) == _lib.EINVAL                # payload drained, connection still usable
+    assert c.put(other, 77, 0) == 0
+    assert c.exists(np.array([77], np.uint64)) == 1 and c.exists(np.array([8, 7, 3], np.uint64)) == 3
+    assert c.stats()["n_used"] == 7                          # 6 chunks of the first model + 1 of the second
+    dst = KVPool(None, 2 * 2 * SLOT, 2 * SLOT, _lib.POOL_CREATE)
+    assert c.get(dst, 77, 0) == 0
+    s2, n2, _ = dst.acquire(77)
+    assert n2 == 256 and int(dst.slot_view(s2)[-1]) == 5
+    dst.release(77)
+    # asking for a chunk of the other geometry is refused (payload drained, connection still usable)
+    assert c.get(other, 8, 0) == _lib.EINVAL and c.get(a, 77, 0) == _lib.EINVAL
     assert c.ping()
     c.close()
 

@@ -194,3 +194,18 @@ def test_config4_kvaware_routes_to_the_instance_holding_the_kv(tmp_path, shm_nam
         for i, p in enumerate(pools):
             p.close()
             KVPool.unlink(f"{shm_name}-{i}")
+
+
+def test_reference_router_unit_tests_pass_on_top_of_the_stubs():
+    """The stand-ins for the absent `uhashring` / `kubernetes` wheels (tests/stubs) must not bend the
+    router's behaviour: the reference's OWN unit tests of session routing (stickiness, minimal movement on
+    add/remove of an endpoint) and round-robin routing pass with them (`@pytest.mark.asyncio` tests run by
+    tests/stubs/pytest_asyncio_shim.py; pytest-asyncio is absent too)."""
+    if not REF_SRC.startswith("/root/reference"):
+        pytest.skip("the reference's test files are only in the reference tree")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "stubs"), REF_SRC]))
+    out = subprocess.run([sys.executable, "-m", "pytest", "-p", "pytest_asyncio_shim", "-p", "no:cacheprovider", "-q",
+                          os.path.join(REF_SRC, "tests", "test_session_router.py"),
+                          os.path.join(REF_SRC, "tests", "test_roundrobin_router.py")],
+                         env=env, capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert out.returncode == 0 and " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-2000:]

@@ -223,9 +223,9 @@ def main():
             for lg in logs:
                 lg.close()
             if mode.startswith("shared"):     # the box-wide segment outlives its replicas: remove it
-                sys.path.insert(0, os.path.join(ROOT, "production-stack_b200"))
-                from b200kv import KVPool
-                KVPool.unlink(f"/b200kv-box-{os.getpid()}-{mode}")
+                import glob
+                for f in glob.glob(f"/dev/shm/b200kv-box-{os.getpid()}-{mode}*"):   # name + "-<chunk bytes>"
+                    os.unlink(f)
             print(json.dumps(res), flush=True)
             results.append(res)
             time.sleep(3)
