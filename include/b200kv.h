@@ -58,6 +58,10 @@ extern "C" {
  *        (helm/templates/deployment-vllm-multi.yaml:341-344).                              */
 #define B200KV_FMT_RAW 0
 #define B200KV_FMT_FP8 1
+/* Q4 (experimental): group-wise 4-bit — per (token, head) groups of 32 elements, bf16 scale = absmax/7,
+ * two's-complement nibbles; a stored token of one plane is [H*D/2 codes][H*D/32 scales] (4.5 bits per
+ * element).  Specified by oracle/kv_oracle.py q4_pack_chunk.  Source dtype bf16, D % 32 == 0.        */
+#define B200KV_FMT_Q4 2
 
 /* ---- order inside one (block, K|V) tile of the paged cache ------------------------------ */
 /* NHD: [block_tokens][H][D] (FlashAttention default, vllm/v1/attention/backends/flash_attn.py:

@@ -335,6 +335,8 @@ class OracleEngine:
             bits = gather_tokens(kv_layers, np.asarray(slot_mapping[s:e]))
             if self.fmt == "fp8":
                 payload = fp8_pack_chunk(bits)
+            elif self.fmt == "q4":
+                payload = q4_pack_chunk(bits)
             else:
                 payload = (bits.copy(),)
             if self.capacity is not None and len(self.pool) >= self.capacity:
@@ -357,7 +359,8 @@ class OracleEngine:
             if ent is None or ent[0] != e - s:
                 break
             self._touch(keys[c])
-            bits = fp8_unpack_chunk(ent[1], ent[2]) if self.fmt == "fp8" else ent[1]
+            bits = (fp8_unpack_chunk(ent[1], ent[2]) if self.fmt == "fp8"
+                    else q4_unpack_chunk(ent[1], ent[2]) if self.fmt == "q4" else ent[1])
             scatter_tokens(kv_layers, bits, np.asarray(slot_mapping[s:e]))
             ret[s:e] = True
         return ret

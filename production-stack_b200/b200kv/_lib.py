@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200kv.so")
 
-FMT_RAW, FMT_FP8 = 0, 1
+FMT_RAW, FMT_FP8, FMT_Q4 = 0, 1, 2   # FMT_Q4: experimental (group-wise 4-bit)
 VARIANT_BULK, VARIANT_LDG = 0, 1
 LAYOUT_NHD, LAYOUT_HND = 0, 1
 POOL_CREATE, POOL_ATTACH, POOL_CREATE_OR_ATTACH = 1, 2, 3

@@ -168,7 +168,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                 atexit.register(KVPool.unlink, self._pool_name)
         logger.info("b200kv connector role=%s kv_role=%s pool=%s (%.1f GB, chunk %d, fmt %s)",
                     role.name, self.kv_role, self._pool_name, self.cfg.max_local_cpu_size_gb, self._chunk,
-                    "fp8" if self.cfg.fmt else "raw")
+                    ("raw", "fp8", "q4")[self.cfg.fmt])
 
     def _make_remote(self, key_seeds):
         """LMCACHE_REMOTE_URL=lm://host:port (deployment-vllm-multi.yaml:338-345): the cache-server

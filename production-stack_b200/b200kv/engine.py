@@ -104,7 +104,11 @@ class KVGeometry:
     def payload_bytes_per_token(self) -> int:
         """Bytes one token occupies in a stored chunk (SURVEY.md §8d 'payload P')."""
         per = 2 * self.n_layers * self.token_bytes
-        return per if self.fmt == FMT_RAW else per // 2
+        if self.fmt == FMT_RAW:
+            return per
+        if self.fmt == FMT_FP8:
+            return per // 2
+        return per * 9 // 32          # Q4: 4 bits + one bf16 scale per 32 elements = 4.5 bits per element
 
 
 class KVPool:

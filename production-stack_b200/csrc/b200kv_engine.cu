@@ -150,6 +150,13 @@ int make_geometry(const b200kv_engine_config* c, Geometry* g) {
     g->scales_off = g->slab_bytes * g->planes;
     g->chunk_bytes = g->scales_off + static_cast<uint64_t>(g->planes) * g->H * sizeof(float);
     g->chunk_bytes = (g->chunk_bytes + 255) / 256 * 256;
+  } else if (c->format == B200KV_FMT_Q4) {
+    if (g->elem != 2) return B200KV_ENOTSUP;
+    if (g->D % 32) return B200KV_EINVAL;
+    g->fmt_token_bytes = g->H * g->D / 2 + g->H * (g->D / 32) * 2;   // one token record of one plane
+    g->slab_bytes = static_cast<uint64_t>(g->C) * g->fmt_token_bytes;
+    g->scales_off = 0;
+    g->chunk_bytes = (g->slab_bytes * g->planes + 255) / 256 * 256;
   } else {
     return B200KV_EINVAL;
   }
@@ -530,6 +537,31 @@ int launch_fp8_load(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& 
 }
 
 // chunk-side copy between staging and the pinned pool; partial chunks move only their tokens.
+int launch_q4(b200kv_ctx* ctx, bool store, const uint8_t* dev_table, const TableView& tv, size_t run_begin,
+              size_t n_runs, cudaStream_t s, uint32_t plane_begin = 0, uint32_t n_planes = 0) {
+  Q4Params p{};
+  p.paged = local_side(ctx);
+  p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off) + run_begin;
+  p.chunk_addrs = reinterpret_cast<const uint64_t*>(dev_table + tv.addrs_off);
+  p.n_runs = static_cast<uint32_t>(n_runs);
+  p.n_planes = n_planes ? n_planes : ctx->g.planes;
+  p.plane_begin = plane_begin;
+  p.chunk_tokens = ctx->g.C;
+  p.n_heads = ctx->g.H;
+  p.head_bytes = ctx->g.D * 2;
+  p.slab_bytes = ctx->g.slab_bytes;
+  p.rec_bytes = ctx->g.fmt_token_bytes;
+  p.hnd = ctx->g.hnd ? 1u : 0u;
+  p.total_units = p.n_runs * p.n_planes;
+  const uint32_t grid = std::min<uint32_t>(p.total_units, static_cast<uint32_t>(ctx->sm_count) * 8u);
+  if (grid == 0) return B200KV_OK;
+  if (store) kv_q4_store_kernel<<<grid, 256, 0, s>>>(p);
+  else kv_q4_load_kernel<<<grid, 256, 0, s>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++ctx->stats.n_kernel_launches;
+  return B200KV_OK;
+}
+
 int copy_chunk(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, cudaMemcpyKind kind,
                cudaStream_t s) {
   const Geometry& g = ctx->g;
@@ -539,7 +571,7 @@ int copy_chunk(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, cuda
     moved = g.chunk_bytes;
   } else {
     // HND keeps whole tiles: a ragged tail still occupies its last tile across all heads
-    const uint32_t tok_span = g.hnd ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
+    const uint32_t tok_span = (g.hnd && ctx->cfg.format != B200KV_FMT_Q4) ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
     const size_t width = static_cast<size_t>(tok_span) * g.fmt_token_bytes;
     CU_TRY(cudaMemcpy2DAsync(dst, g.slab_bytes, src, g.slab_bytes, width, g.planes, kind, s));
     moved = width * g.planes;
@@ -567,7 +599,7 @@ int copy_chunk_planes(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_to
     moved = static_cast<uint64_t>(np) * g.slab_bytes;
     CU_TRY(cudaMemcpyAsync(d, sp, moved, kind, s));
   } else {
-    const uint32_t tok_span = g.hnd ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
+    const uint32_t tok_span = (g.hnd && ctx->cfg.format != B200KV_FMT_Q4) ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
     const size_t width = static_cast<size_t>(tok_span) * g.fmt_token_bytes;
     CU_TRY(cudaMemcpy2DAsync(d, g.slab_bytes, sp, g.slab_bytes, width, np, kind, s));
     moved = width * np;
@@ -826,7 +858,7 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   const uint32_t n_chunks = static_cast<uint32_t>((n_tokens + g.C - 1) / g.C);
 
   std::vector<Run> runs, partial;
-  const bool fp8 = ctx->cfg.format == B200KV_FMT_FP8;
+  const bool fp8 = ctx->cfg.format != B200KV_FMT_RAW;   // one sorted run list for every transformed format
   int rc = build_runs(ctx, slots, 0, n_tokens, 0, &runs, fp8 ? nullptr : &partial);
   if (rc) return rc;
   const size_t n_full = runs.size(), n_part = partial.size();
@@ -855,6 +887,8 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   if (ctx->cfg.format == B200KV_FMT_FP8) {
     rc = is_gather ? launch_fp8_store(ctx, tv.slot->dev, tv, n_chunks, static_cast<uint32_t>(n_tokens), s)
                    : launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), s);
+  } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+    rc = launch_q4(ctx, is_gather, tv.slot->dev, tv, 0, runs.size(), s);
   } else {
     rc = is_gather ? launch_copy_runs<kStore>(ctx, tv.slot->dev, tv, 0, n_full, n_part, s)
                    : launch_copy_runs<kLoad>(ctx, tv.slot->dev, tv, 0, n_full, n_part, s);
@@ -992,7 +1026,7 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       // dense op-relative token index: chunk i of this batch starts at i*C
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs,
-                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &partial);
+                          ctx->cfg.format != B200KV_FMT_RAW ? nullptr : &partial);
       if (rc) return rc;
       sidx[i] = ctx->store_next;
       ctx->store_next = (ctx->store_next + 1) % static_cast<uint32_t>(n_stage);
@@ -1017,6 +1051,8 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
     if (ctx->cfg.format == B200KV_FMT_FP8) {
       // a partial chunk is always the last of the op, hence the last of its batch
       rc = launch_fp8_store(ctx, tv.slot->dev, tv, static_cast<uint32_t>(nb), batch_tokens, ctx->s_gather);
+    } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+      rc = launch_q4(ctx, true, tv.slot->dev, tv, 0, runs.size(), ctx->s_gather);
     } else {
       rc = launch_copy_runs<kStore>(ctx, tv.slot->dev, tv, 0, n_full, n_part, ctx->s_gather);
     }
@@ -1120,7 +1156,7 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       std::vector<Run> cf, cp;
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf,
-                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &cp);
+                          ctx->cfg.format != B200KV_FMT_RAW ? nullptr : &cp);
       if (rc) return rc;
       n_full_of[i] = static_cast<uint32_t>(cf.size());
       runs.insert(runs.end(), cf.begin(), cf.end());
@@ -1159,6 +1195,8 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       if (rc) return rc;
       if (ctx->cfg.format == B200KV_FMT_FP8) {
         rc = launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), ctx->s_scatter, pb, np);
+      } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+        rc = launch_q4(ctx, false, tv.slot->dev, tv, 0, runs.size(), ctx->s_scatter, pb, np);
       } else {
         // one launch per chunk keeps the (full, partial) run split of each chunk
         for (size_t i = 0; i < nb && rc == B200KV_OK; ++i)
@@ -1191,7 +1229,7 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       std::vector<Run> cf, cp;  // per chunk: whole tiles first, then HND partial-tile runs
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf,
-                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &cp);
+                          ctx->cfg.format != B200KV_FMT_RAW ? nullptr : &cp);
       if (rc) return rc;
       n_full_of[i] = static_cast<uint32_t>(cf.size());
       runs.insert(runs.end(), cf.begin(), cf.end());
@@ -1224,6 +1262,8 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       const size_t r0 = offs[i], rn = offs[i + 1] - offs[i];
       if (ctx->cfg.format == B200KV_FMT_FP8) {
         rc = launch_fp8_load(ctx, tv.slot->dev, tv, r0, rn, ctx->s_scatter);
+      } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+        rc = launch_q4(ctx, false, tv.slot->dev, tv, r0, rn, ctx->s_scatter);
       } else {
         rc = launch_copy_runs<kLoad>(ctx, tv.slot->dev, tv, r0, n_full_of[i], rn - n_full_of[i], ctx->s_scatter);
       }

@@ -810,4 +810,102 @@ __global__ void __launch_bounds__(kFp8Threads) kv_fp8_load_kernel(const Fp8LoadP
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Q4: group-wise 4-bit format (B200KV_FMT_Q4; oracle: q4_pack_chunk / q4_unpack_chunk).  A stored
+// token of one plane is a record [H*D/2 code bytes][H*D/32 bf16 scales]; records are token-major in the
+// slab whatever the order inside the paged tiles.  One 16-byte vector (8 elements) per thread, a group
+// of 32 elements = 4 adjacent lanes: absmax by two shuffles, no shared memory, no cluster.
+// EXPERIMENTAL: written against the oracle, not yet run on a GPU.
+// ---------------------------------------------------------------------------------------------
+struct Q4Params {
+  PagedSide paged;
+  const Run* runs;
+  const uint64_t* chunk_addrs;
+  uint32_t n_runs, n_planes, plane_begin;
+  uint32_t chunk_tokens;
+  uint32_t n_heads, head_bytes;   // head_bytes = D*2 (bf16 side)
+  uint64_t slab_bytes;            // C * rec_bytes
+  uint32_t rec_bytes;             // H*D/2 + H*D/32*2
+  uint32_t total_units;           // n_runs * n_planes
+  uint32_t hnd;
+};
+
+__device__ __forceinline__ uint64_t q4_src_addr(const Q4Params& p, uint32_t plane, uint32_t slot, uint32_t v) {
+  // v = 16-byte vector index inside the token: head h = v / rv, vector c of that head
+  if (!p.hnd) return paged_addr(p.paged, plane, slot) + static_cast<uint64_t>(v) * 16;
+  const uint32_t rv = p.head_bytes >> 4;
+  const uint32_t h = v / rv, c = v - h * rv;
+  return paged_addr_hnd(p.paged, plane, slot, h, p.head_bytes) + static_cast<uint64_t>(c) * 16;
+}
+
+__global__ void __launch_bounds__(256) kv_q4_store_kernel(const Q4Params p) {
+  const uint32_t vpt = (p.n_heads * p.head_bytes) >> 4;      // vectors per token (multiple of 4)
+  const uint32_t codes_bytes = vpt * 4;
+  for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x) {
+    const uint32_t plane = p.plane_begin + ui % p.n_planes;
+    const Run run = p.runs[ui / p.n_planes];
+    const uint32_t c = static_cast<uint32_t>(run.b) / p.chunk_tokens;
+    const uint32_t t0 = static_cast<uint32_t>(run.b) - c * p.chunk_tokens;
+    uint8_t* slab = reinterpret_cast<uint8_t*>(__ldg(p.chunk_addrs + c) + static_cast<uint64_t>(plane) * p.slab_bytes);
+    const uint32_t nvec = static_cast<uint32_t>(run.n) * vpt;
+    for (uint32_t base = 0; base < nvec; base += 256) {   // uniform trip count: every lane takes part in the shuffles
+      const uint32_t idx = base + threadIdx.x;             // 256 and vpt are multiples of 4: quads stay whole
+      const bool ok = idx < nvec;
+      const uint32_t t = ok ? idx / vpt : 0, v = ok ? idx - t * vpt : 0;
+      const uint4 x = ok ? ld_nc_v4(reinterpret_cast<const void*>(q4_src_addr(p, plane, static_cast<uint32_t>(run.a) + t, v)))
+                         : make_uint4(0, 0, 0, 0);
+      uint32_t acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(0u, x.x), x.y), x.z), x.w);
+      uint32_t m = max(acc & 0xffffu, acc >> 16);
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      const float amax = __uint_as_float(m << 16);
+      const __nv_bfloat16 sb = m ? __float2bfloat16_rn(__fdiv_rn(amax, 7.0f)) : __float2bfloat16_rn(1.0f);
+      const float s = __bfloat162float(sb);
+      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+      uint32_t packed = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+        const int ql = max(-7, min(7, __float2int_rn(__fdiv_rn(lo, s))));
+        const int qh = max(-7, min(7, __float2int_rn(__fdiv_rn(hi, s))));
+        packed |= (static_cast<uint32_t>(ql & 0xF) | (static_cast<uint32_t>(qh & 0xF) << 4)) << (8 * i);
+      }
+      if (!ok) continue;
+      uint8_t* rec = slab + static_cast<uint64_t>(t0 + t) * p.rec_bytes;
+      *reinterpret_cast<uint32_t*>(rec + static_cast<size_t>(v) * 4) = packed;
+      if ((v & 3u) == 0) *reinterpret_cast<__nv_bfloat16*>(rec + codes_bytes + static_cast<size_t>(v >> 2) * 2) = sb;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) kv_q4_load_kernel(const Q4Params p) {
+  const uint32_t vpt = (p.n_heads * p.head_bytes) >> 4;
+  const uint32_t codes_bytes = vpt * 4;
+  for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x) {
+    const uint32_t plane = p.plane_begin + ui % p.n_planes;
+    const Run run = p.runs[ui / p.n_planes];
+    const uint32_t c = static_cast<uint32_t>(run.b) / p.chunk_tokens;
+    const uint32_t t0 = static_cast<uint32_t>(run.b) - c * p.chunk_tokens;
+    const uint8_t* slab =
+        reinterpret_cast<const uint8_t*>(__ldg(p.chunk_addrs + c) + static_cast<uint64_t>(plane) * p.slab_bytes);
+    const uint32_t nvec = static_cast<uint32_t>(run.n) * vpt;
+    for (uint32_t idx = threadIdx.x; idx < nvec; idx += 256) {
+      const uint32_t t = idx / vpt, v = idx - t * vpt;
+      const uint8_t* rec = slab + static_cast<uint64_t>(t0 + t) * p.rec_bytes;
+      const uint32_t packed = *reinterpret_cast<const uint32_t*>(rec + static_cast<size_t>(v) * 4);
+      const float s = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rec + codes_bytes + static_cast<size_t>(v >> 2) * 2));
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = static_cast<int>((packed >> (8 * i)) & 0xffu);
+        const int ql = ((b & 0xF) ^ 8) - 8, qh = ((b >> 4) ^ 8) - 8;   // sign-extend the nibbles
+        const __nv_bfloat162 r = __floats2bfloat162_rn(static_cast<float>(ql) * s, static_cast<float>(qh) * s);
+        o[i] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+      st_na_v4(reinterpret_cast<void*>(q4_src_addr(p, plane, static_cast<uint32_t>(run.a) + t, v)),
+               make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
 }  // namespace b200kv
