@@ -61,7 +61,7 @@ def main():
     from vllm.distributed.kv_transfer.kv_connector.v1.lmcache_integration import vllm_v1_adapter as A
     rng = np.random.default_rng(20260921)
     scenarios = []
-    for sid in range(160):
+    for sid in range(int(os.environ.get("GOLDEN_SCENARIOS", "160"))):
         bs = 16
         chunk = int(rng.choice([64, 256]))
         prompt_len = int(rng.choice([1, 15, 16, chunk - 1, chunk, chunk + 1, 2 * chunk, 2 * chunk + 37,
@@ -126,7 +126,7 @@ def main():
     import vllm
     doc = {"source": "vllm %s lmcache_integration/vllm_v1_adapter.py RequestTracker + ReqMeta.from_request_tracker, "
                      "executed by tests/golden/make_adapter_golden.py" % vllm.__version__, "scenarios": scenarios}
-    with open(os.path.join(HERE, "adapter_plan_vectors.json"), "w") as f:
+    with open(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "adapter_plan_vectors.json"), "w") as f:
         json.dump(doc, f, separators=(",", ":"))
     n_steps = sum(len(s["steps"]) for s in scenarios)
     n_meta = sum(st["meta"] is not None for s in scenarios for st in s["steps"])
@@ -155,7 +155,7 @@ def main_flows():
     import torch
     torch.Tensor.cuda = lambda self, *a, **k: self       # the worker methods move slot mappings to the GPU
     flows = []
-    for fid in range(60):
+    for fid in range(int(os.environ.get("GOLDEN_FLOWS", "60"))):
         bs = 16
         chunk = int(rng.choice([64, 256]))
         discard = bool(rng.integers(0, 2))
@@ -289,7 +289,7 @@ def main_flows():
     doc = {"source": "vllm %s lmcache_integration/vllm_v1_adapter.py LMCacheConnectorV1Impl.get_num_new_matched_tokens / "
                      "update_state_after_alloc / build_connector_meta, executed by tests/golden/make_adapter_golden.py flows"
                      % vllm.__version__, "flows": flows}
-    with open(os.path.join(HERE, "adapter_flow_vectors.json"), "w") as f:
+    with open(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "adapter_flow_vectors.json"), "w") as f:
         json.dump(doc, f, separators=(",", ":"))
     print(len(flows), "flows,", sum(len(f["steps"]) for f in flows), "steps,",
           sum(len(s["metas"]) for f in flows for s in f["steps"]), "metas")

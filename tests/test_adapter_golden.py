@@ -12,11 +12,12 @@ from b200kv.adapter import LoadSpec, RequestTracker, make_req_meta
 from b200kv.engine import xxh64
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.environ.get("GOLDEN_OUT") or os.path.join(HERE, "golden")   # GOLDEN_OUT: a larger, uncommitted sweep
 
 
 def test_planning_matches_the_vendored_lmcache_adapter_step_by_step():
-    doc = json.load(open(os.path.join(HERE, "golden", "adapter_plan_vectors.json")))
-    assert "vllm_v1_adapter.py" in doc["source"] and len(doc["scenarios"]) == 160
+    doc = json.load(open(os.path.join(GOLDEN, "adapter_plan_vectors.json")))
+    assert "vllm_v1_adapter.py" in doc["source"] and len(doc["scenarios"]) >= 160
     n_meta = n_load = 0
     for sc in doc["scenarios"]:
         bs, chunk = sc["block_size"], sc["chunk"]
@@ -85,8 +86,8 @@ def test_scheduler_flows_match_the_vendored_connector_impl():
         def poll(self, t):
             return True
 
-    doc = json.load(open(os.path.join(HERE, "golden", "adapter_flow_vectors.json")))
-    assert "LMCacheConnectorV1Impl" in doc["source"] and len(doc["flows"]) == 60
+    doc = json.load(open(os.path.join(GOLDEN, "adapter_flow_vectors.json")))
+    assert "LMCacheConnectorV1Impl" in doc["source"] and len(doc["flows"]) >= 60
     n_meta = n_need = n_calls = 0
     for fl in doc["flows"]:
         bs, chunk = fl["block_size"], fl["chunk"]
@@ -138,4 +139,4 @@ def test_scheduler_flows_match_the_vendored_connector_impl():
                 want_calls = [c for c in st["engine_calls"] if not (c[0] == "store" and c[4] >= c[1])]
                 assert rec.calls == want_calls, (fl["id"], si)
                 n_calls += len(want_calls)
-    assert n_meta == 160 and n_need > 10 and n_calls > 50
+    assert n_meta >= 160 and n_need > 10 and n_calls > 50

@@ -1,7 +1,10 @@
 """Multi-round-QA workload driver — a restatement (not a copy) of the reference harness
 benchmarks/multi-round-qa/multi-round-qa.py for the GPU box, where /root/reference does not exist.
-Where the reference tree is available (this build container) the unmodified harness is what
-tests/test_router_plumbing.py drives; this driver produces the same traffic shape:
+Where the reference tree is available (this build container) tests/test_e2e_tooling.py runs the
+unmodified harness and this driver against a recording mock backend and requires byte-identical
+`messages`, max_tokens, stream flag and x-user-id header for every (session, turn) they share (the
+harness's first `num_users` sessions start mid-conversation, a ramp-up this driver does not imitate).
+The traffic shape:
 
 * first turn = "Hi, here's some system prompt: " + "hi "*S + "For user <id>, here are some other
   context: " + "hi "*U + question            (multi-round-qa.py:232-251)

@@ -51,6 +51,43 @@ def connector_args(mode: str, cpu_gb: float):
     raise ValueError(mode)
 
 
+def harness_path() -> str | None:
+    """The UNMODIFIED benchmarks/multi-round-qa/multi-round-qa.py: in the reference tree, or — on the GPU box —
+    the byte-identical copy `__graft_entry__.build()` placed in the git-ignored baseline/_ref."""
+    for p in ("/root/reference/benchmarks/multi-round-qa/multi-round-qa.py",
+              os.path.join(ROOT, "baseline", "_ref", "benchmarks", "multi-round-qa", "multi-round-qa.py")):
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def run_harness(base_url: str, model: str, a, out_csv: str, seconds: float) -> dict:
+    """Drive the engine with the unmodified harness; p50 TTFT comes from the per-request CSV it writes
+    (the harness itself prints the MEAN, multi-round-qa.py:497,526)."""
+    import csv
+    import statistics
+    hp = harness_path()
+    cmd = [sys.executable, hp, "--num-users", str(a.num_users), "--num-rounds", str(a.num_rounds), "--qps", str(a.qps),
+           "--shared-system-prompt", str(a.shared_system_prompt), "--user-history-prompt", str(a.user_history_prompt),
+           "--answer-len", str(a.answer_len), "--model", model, "--base-url", base_url, "--time", str(int(seconds)),
+           "--request-with-user-id", "--output", out_csv]
+    t0 = time.time()
+    out = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(out_csv) or ".")
+    wall = time.time() - t0
+    rows = list(csv.DictReader(open(out_csv))) if os.path.exists(out_csv) else []
+    ttft = sorted(float(r["ttft"]) for r in rows)
+    later = sorted(float(r["ttft"]) for r in rows if int(float(r["question_id"])) > 1)
+    gen = sum(float(r["generation_tokens"]) for r in rows)
+    span = (max(float(r["finish_time"]) for r in rows) - min(float(r["launch_time"]) for r in rows)) if rows else 0
+    return {"driver": "unmodified harness " + hp, "harness_exit": out.returncode, "requests": len(rows), "wall_s": wall,
+            "ttft_p50_s": statistics.median(ttft) if ttft else None,
+            "ttft_mean_s": statistics.fmean(ttft) if ttft else None,
+            "ttft_p50_later_turns_s": statistics.median(later) if later else None,
+            "ttft_p90_s": ttft[int(0.9 * (len(ttft) - 1))] if ttft else None,
+            "output_tokens_per_s": gen / span if span > 0 else None,
+            "harness_tail": out.stdout[-600:] if out.returncode else ""}
+
+
 def wait_ready(port: int, proc: subprocess.Popen, timeout: float, host: str = "127.0.0.1") -> bool:
     t0 = time.time()
     while time.time() - t0 < timeout:
@@ -81,7 +118,13 @@ def main():
                  ("--user-history-prompt", 1536), ("--answer-len", 64)):
         ap.add_argument(a, type=int, default=d)
     ap.add_argument("--qps", type=float, default=2.0)
+    ap.add_argument("--harness", action="store_true",
+                    help="drive with the unmodified benchmarks/multi-round-qa harness for --harness-time seconds "
+                         "instead of tools/e2e/mrqa_driver.py")
+    ap.add_argument("--harness-time", type=float, default=60.0)
     args = ap.parse_args()
+    if args.harness and harness_path() is None:
+        raise SystemExit("--harness: the reference harness is neither under /root/reference nor in baseline/_ref")
     os.makedirs(args.log_dir, exist_ok=True)
     subprocess.run([sys.executable, os.path.join(HERE, "make_model.py"), args.model_dir, "--layers", str(args.layers),
                     "--max-len", str(max(args.max_model_len, 8192))], check=True, stdout=subprocess.DEVNULL)
@@ -114,12 +157,16 @@ def main():
                 # warm-up like the harness (10 short requests, multi-round-qa.py:552-561)
                 w = argparse.Namespace(**{**vars(d), "num_users": 4, "num_rounds": 1, "shared_system_prompt": 50,
                                           "user_history_prompt": 50, "answer_len": 8, "qps": 8.0, "init_user_id": 9000})
-                asyncio.run(mrqa_driver.run(w))
-                rows, summary = asyncio.run(mrqa_driver.run(d))
-                res.update(summary)
-                with open(os.path.join(args.log_dir, f"mrqa_rows_{mode}.jsonl"), "w") as f:
-                    for r in rows:
-                        f.write(json.dumps(r) + "\n")
+                if args.harness:      # the harness does its own warm-up (10 short requests, :552-561)
+                    res.update(run_harness(f"http://127.0.0.1:{args.port}/v1", "synth-llama3-8b", args,
+                                           os.path.join(args.log_dir, f"harness_{mode}.csv"), args.harness_time))
+                else:
+                    asyncio.run(mrqa_driver.run(w))
+                    rows, summary = asyncio.run(mrqa_driver.run(d))
+                    res.update(summary)
+                    with open(os.path.join(args.log_dir, f"mrqa_rows_{mode}.jsonl"), "w") as f:
+                        for r in rows:
+                            f.write(json.dumps(r) + "\n")
                 try:
                     with urllib.request.urlopen(f"http://127.0.0.1:{args.port}/metrics", timeout=5) as r:
                         txt = r.read().decode()

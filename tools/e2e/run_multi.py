@@ -48,7 +48,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 import mrqa_driver  # noqa: E402
-from run_e2e import wait_ready  # noqa: E402
+from run_e2e import harness_path, run_harness, wait_ready  # noqa: E402
 
 MODEL = "synth-llama3-8b"
 
@@ -121,6 +121,9 @@ def main():
                          "after the other, --gpu-mem-util split between them; timings are not per-replica numbers)")
     ap.add_argument("--extra", default="", help="extra vllm serve args, e.g. --extra=--enforce-eager")
     ap.add_argument("--kv-aware-threshold", type=int, default=2000)
+    ap.add_argument("--harness", action="store_true",
+                    help="drive with the unmodified multi-round-qa harness (chat API; not for --routing kvaware / pd)")
+    ap.add_argument("--harness-time", type=float, default=60.0)
     ap.add_argument("--mock", action="store_true", help="orchestration dry run: tools/mock_backend.py instead of vllm (no GPU)")
     args = ap.parse_args()
     os.makedirs(args.log_dir, exist_ok=True)
@@ -209,12 +212,16 @@ def main():
             w = argparse.Namespace(**{**vars(d), "num_users": 2 * args.replicas, "num_rounds": 1,
                                       "shared_system_prompt": 50, "user_history_prompt": 50, "answer_len": 8,
                                       "qps": 8.0, "init_user_id": 9000})
-            asyncio.run(mrqa_driver.run(w))
-            rows, summary = asyncio.run(mrqa_driver.run(d))
-            res.update(summary)
-            with open(os.path.join(args.log_dir, f"mrqa_rows_{mode}.jsonl"), "w") as f:
-                for r in rows:
-                    f.write(json.dumps(r) + "\n")
+            if args.harness and args.routing not in ("kvaware", "pd") and harness_path():
+                res.update(run_harness("http://127.0.0.1:8090/v1", model_name, args,
+                                       os.path.join(args.log_dir, f"harness_{mode}.csv"), args.harness_time))
+            else:
+                asyncio.run(mrqa_driver.run(w))
+                rows, summary = asyncio.run(mrqa_driver.run(d))
+                res.update(summary)
+                with open(os.path.join(args.log_dir, f"mrqa_rows_{mode}.jsonl"), "w") as f:
+                    for r in rows:
+                        f.write(json.dumps(r) + "\n")
             res["replica_metrics"] = [scrape(p, host=h) for p, h in zip(ports, hosts)]
             res["router_requests_per_backend"] = scrape(8090, ("vllm:num_incoming_requests", "current_qps", "num_requests"))
         finally:

@@ -7,6 +7,7 @@ vLLM protocol modules that no longer exist in vLLM 0.22.
 """
 import argparse
 import asyncio
+import hashlib
 import json
 import time
 
@@ -52,8 +53,11 @@ async def tokenize(req: Request):
 
 
 def _record(req: Request, body: dict):
+    full = str(body.get("prompt", ""))
     STATE["served"].append({"id": req.headers.get("x-request-id"), "user": req.headers.get("x-user-id"),
-                            "t": time.time(), "prompt": str(body.get("prompt", ""))[:64]})
+                            "t": time.time(), "prompt": full[:64], "sha1": hashlib.sha1(full.encode()).hexdigest(),
+                            "n_messages": body.get("n_messages"), "max_tokens": body.get("max_tokens"),
+                            "stream": bool(body.get("stream"))})
 
 
 @app.post("/v1/completions")
@@ -81,7 +85,8 @@ async def completions(req: Request):
 @app.post("/v1/chat/completions")
 async def chat(req: Request):
     body = await req.json()
-    _record(req, {"prompt": json.dumps(body.get("messages", []))})
+    _record(req, {"prompt": json.dumps(body.get("messages", [])), "n_messages": len(body.get("messages", [])),
+                  "max_tokens": body.get("max_tokens"), "stream": body.get("stream")})
     n = int(body.get("max_tokens", 8))
     if body.get("stream"):
         async def gen():

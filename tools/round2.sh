@@ -17,6 +17,8 @@ case "$stage" in
       B200KV_FP8_2PASS=1 python tools/microbench.py --out "$out/microbench_2pass.json" > "$out/microbench_2pass.log" 2>&1
     fi
     python bench.py > "$out/bench_n1.json" 2> "$out/bench_n1.err"
+    # BASELINE configs[1] with the UNMODIFIED harness (reference numbers so far came from tools/e2e/mrqa_driver.py)
+    python tools/e2e/run_e2e.py --harness --harness-time 90 --modes none,b200kv,offload --log-dir "$out/e2e_harness" 2>&1 | cut -c1-500
     tail -c 400 "$out/bench_n1.json"
     ;;
   multi2)
