@@ -16,7 +16,10 @@ tests/e2e/test-routing.py:471-475 returns True unconditionally).  What IS pinned
   the inverse at :154-159), evaluated with torch;
 * XXH64                      — the ``xxhash`` wheel the reference's prefix router uses
   (/root/reference/src/vllm_router/prefix/hashtrie.py:56-57);
-* e4m3 rounding              — ``ml_dtypes.float8_e4m3fn`` / ``torch.float8_e4m3fn`` casts.
+* e4m3 rounding              — ``ml_dtypes.float8_e4m3fn`` / ``torch.float8_e4m3fn`` casts;
+* save / load planning and the engine calling convention (``plan_save``, ``num_new_matched_tokens``
+  here; ``b200kv.adapter`` in the product) — vLLM's vendored LMCache adapter EXECUTED
+  (``tests/golden/make_adapter_golden.py`` -> ``adapter_plan_vectors.json``, ``adapter_flow_vectors.json``).
 
 Each function cites the file:line whose behaviour it restates.  [vllm-0.22] means the vLLM wheel
 in this image (its vendored LMCache adapter is the only executable description of how the

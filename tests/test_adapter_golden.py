@@ -10,6 +10,7 @@ import numpy as np
 
 from b200kv.adapter import LoadSpec, RequestTracker, make_req_meta
 from b200kv.engine import xxh64
+from oracle import kv_oracle as ko
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.environ.get("GOLDEN_OUT") or os.path.join(HERE, "golden")   # GOLDEN_OUT: a larger, uncommitted sweep
@@ -34,6 +35,14 @@ def test_planning_matches_the_vendored_lmcache_adapter_step_by_step():
                 cur = len(tr.token_ids)
                 tr.update(tokens[cur: cur + st["new_tokens"]], (st["new_blocks"],) if st["new_blocks"] else None)
                 spec = None
+            # the oracle's own restatement of the rule (oracle.plan_save) is pinned by the same vectors
+            plan = ko.plan_save(len(tr.token_ids), sc["prompt_len"], tr.num_saved_tokens, chunk, sc["discard_partial_chunks"],
+                                tr.is_decode_phase, sc["save_decode_cache"], tr.skip_save)
+            ref_saves = st["meta"] is not None and st["meta"]["save"][1]
+            if plan is None:
+                assert (not ref_saves) or st["num_saved_tokens_after"] <= st["meta"]["save"][0] // chunk * chunk, (sc["id"], "oracle")
+            else:
+                assert ref_saves and plan == (st["meta"]["save"][0] // chunk * chunk, st["num_saved_tokens_after"]), (sc["id"], "oracle")
             m = make_req_meta(tr, bs, chunk, spec, sc["discard_partial_chunks"], sc["save_decode_cache"])
             where = (sc["id"], sc["steps"].index(st))
             assert tr.num_saved_tokens == st["num_saved_tokens_after"], where
@@ -106,6 +115,8 @@ def test_scheduler_flows_match_the_vendored_connector_impl():
                 reqs[n["rid"]] = req
                 need = sched.num_new_matched_tokens(n["rid"], req.prompt_token_ids, n["prompt_len"], n["num_computed_before"])
                 assert need == n["need"], (fl["id"], si, n["rid"])
+                if fl["kv_role"] != "kv_producer":       # the oracle's restatement of the same arithmetic
+                    assert ko.num_new_matched_tokens(n["hit"], n["num_computed_before"], n["prompt_len"]) == n["need"]
                 n_need += need > 0
                 sched.after_alloc(req, need)
                 new.append(NS(req_id=n["rid"], prompt_token_ids=req.prompt_token_ids, block_ids=(list(n["blocks"]),),

@@ -267,3 +267,45 @@ def test_shared_pool_name_is_per_geometry(monkeypatch):
     assert pool_name_for(None, cfg, 0x2000000) == "/box-2000000"
     assert pool_name_for(None, cfg, 0x1000800) == "/box-1000800"
     assert pool_name_for(NS(kv_transfer_config=NS(engine_id="e-1/x")), B200KVConfig(), 123) == "/b200kv-e-1x"
+
+
+@pytest.mark.parametrize("backend,layout", [("flashinfer", "HND"), ("flashinfer", "NHD"), ("flash_attn", "NHD"),
+                                            ("flash_attn", "HND")])
+def test_layout_detection_on_tensors_built_like_vllms_model_runner(backend, layout):
+    """The physical KV layouts the engine must understand are whatever vLLM allocates: the attention
+    backend's `get_kv_cache_shape` permuted by its `get_kv_cache_stride_order`, then viewed back in the logical
+    order (vllm/v1/worker/gpu_model_runner.py:6935-6990; backends: v1/attention/backends/flashinfer.py,
+    flash_attn.py).  Built here with vLLM's own functions (CPU tensors) and handed to `paged_layout_of`."""
+    import torch
+    from vllm.v1.attention.backends import utils as U
+
+    from b200kv import _lib
+    from b200kv.engine import paged_layout_of
+    if backend == "flashinfer":
+        from vllm.v1.attention.backends.flashinfer import FlashInferBackend as B
+    else:
+        from vllm.v1.attention.backends.flash_attn import FlashAttentionBackend as B
+    NB, bs, H, D = 12, 16, 8, 128
+    U.set_kv_cache_layout(layout)
+    try:
+        U.get_kv_cache_layout.cache_clear() if hasattr(U.get_kv_cache_layout, "cache_clear") else None
+        shape = B.get_kv_cache_shape(NB, bs, H, D)
+        order = B.get_kv_cache_stride_order()
+    finally:
+        U.set_kv_cache_layout(None)
+        U.get_kv_cache_layout.cache_clear() if hasattr(U.get_kv_cache_layout, "cache_clear") else None
+    phys = tuple(shape[i] for i in order)
+    inv = [order.index(i) for i in range(len(order))]
+    raw = torch.arange(int(np.prod(shape)), dtype=torch.int32).to(torch.bfloat16)
+    t = raw.view(phys).permute(*inv)                          # exactly what the model runner registers
+    assert tuple(t.shape) == tuple(shape)
+    k, v, stride, nb, h, d, tile = paged_layout_of(t, bs)
+    assert (nb, h, d) == (NB, H, D)
+    assert tile == (_lib.LAYOUT_HND if layout == "HND" else _lib.LAYOUT_NHD)
+    es = t.element_size()
+    # K and V planes of block b, and the element (token j, head g, dim e) inside a tile, where vLLM put them
+    for b, j, g, e in [(0, 0, 0, 0), (3, 5, 2, 7), (NB - 1, bs - 1, H - 1, D - 1)]:
+        for kv, base in ((0, k), (1, v)):
+            want = (t[kv, b, j, g, e] if tuple(shape)[0] == 2 else t[b, kv, j, g, e]).data_ptr()
+            inner = (g * bs * D + j * D + e) if tile == _lib.LAYOUT_HND else (j * H * D + g * D + e)
+            assert base + b * stride + inner * es == want, (backend, layout, kv, b, j, g, e)
