@@ -230,7 +230,18 @@ class SchedulerState:
             else:
                 new_tokens = []
             resumed = rid in getattr(cached, "resumed_req_ids", ())
-            tr.update(new_tokens, cached.new_block_ids[i], resumed)
+            if resumed:
+                # Preempted and scheduled again: vLLM recomputes from `num_computed_tokens` (whatever its prefix
+                # cache still holds) into a NEW set of blocks (CachedRequestData, vllm/v1/core/sched/output.py:
+                # 112-126).  Restart the tracker's view of the sequence; what was saved stays saved.  (The
+                # reference adapter appends the new blocks to the old ones here, adapter :214-245.)
+                n_comp = cached.num_computed_tokens[i] if getattr(cached, "num_computed_tokens", None) else 0
+                ids = req.all_token_ids if req is not None else getattr(cached, "all_token_ids", {}).get(rid, tr.token_ids)
+                tr.token_ids = list(ids[: n_comp + n_new])
+                tr.allocated_block_ids = first_group(cached.new_block_ids[i])
+                tr.is_decode_phase = False
+            else:
+                tr.update(new_tokens, cached.new_block_ids[i], False)
             m = make_req_meta(tr, self.block_size, self.chunk, None, self.discard_partial_chunks,
                               self.save_decode_cache)
             if m is not None:

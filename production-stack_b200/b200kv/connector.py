@@ -105,6 +105,13 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                  kv_cache_config: "KVCacheConfig | None" = None):
         super().__init__(vllm_config=vllm_config, role=role, kv_cache_config=kv_cache_config)
         ktc = vllm_config.kv_transfer_config
+        groups = getattr(kv_cache_config, "kv_cache_groups", None)
+        if groups is not None and len(groups) > 1:
+            # one paged cache per layer with ONE block table per request is what this engine moves; with several
+            # KV-cache groups (hybrid / sliding-window models) block ids differ per group — refuse rather than
+            # store pages under the wrong ids
+            raise ValueError(f"B200KVConnector supports a single KV-cache group, the model has {len(groups)}: "
+                             "start vLLM with --disable-hybrid-kv-cache-manager")
         self.cfg = B200KVConfig.from_env().apply_extra(ktc.kv_connector_extra_config)
         self.kv_role = ktc.kv_role
         self._block_size = vllm_config.cache_config.block_size
@@ -427,6 +434,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         # Offload: the gather that reads a request's pages is ordered before any later forward pass
         # on the compute stream, so blocks may be freed immediately.  Disaggregated prefill: keep
         # the pages (delay_free) until the decoder has pulled them (b200kv/pd.py).
+        self._remote_computed.pop(request.request_id, None)   # looked up as a remote prefill but never allocated
         if self._remote is not None:
             self._remote.forget(request.request_id)
         if self._pd is not None:

@@ -328,3 +328,34 @@ def test_priority_limit_serves_but_does_not_save_low_priority_requests():
         n = len(eng.calls)
         w.save(sched.build_meta(sched_out([new_req(rid, prompt, list(range(8)))], num_sched={rid: len(prompt)})))
         assert (len(eng.calls) > n) == stored, rid
+
+
+def test_preempted_request_restarts_on_its_new_blocks():
+    """A request preempted mid-prefill comes back in `scheduled_cached_reqs` with `resumed_req_ids`, ALL of
+    its block ids replaced and `num_computed_tokens` reset (vllm/v1/core/sched/output.py:112-126).  What the
+    connector saves afterwards must be addressed through the new blocks, and nothing already saved is saved
+    twice."""
+    eng = OracleBackedEngine([np.zeros((2, 64, BS, 1, 8), np.uint16)])
+    sched = SchedulerState(lambda t: 0, BS, C, False)
+    w = WorkerState(eng, BS, C)
+    prompt = list(range(1, 3 * C + 10))                                     # 202 tokens
+    req = NS(request_id="p", prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt)
+    sched.num_new_matched_tokens("p", prompt, len(prompt), 0)
+    sched.after_alloc(req, 0)
+    old_blocks = list(range(0, 7))
+    metas = sched.build_meta(sched_out([new_req("p", prompt, old_blocks)], num_sched={"p": 100}))
+    w.save(metas)
+    assert eng.calls == [("store", C, 0)]                                    # chunk 0 saved from the old blocks
+    new_blocks = list(range(20, 33))
+    cached = NS(req_ids=["p"], new_block_ids=[(new_blocks,)], resumed_req_ids={"p"}, all_token_ids={},
+                num_computed_tokens=[0])
+    metas = sched.build_meta(sched_out(cached=cached, num_sched={"p": len(prompt)}))   # the whole prompt again
+    (m,) = metas
+    assert m.block_ids == new_blocks and len(m.token_ids) == len(prompt) and m.is_last_prefill
+    assert list(m.slot_mapping(BS)[:3]) == [20 * BS, 20 * BS + 1, 20 * BS + 2]
+    w.save(metas)
+    assert eng.calls[-1] == ("store", len(prompt), C)                         # chunks 1.. only; chunk 0 is not re-saved
+    # and it decodes normally afterwards
+    req.all_token_ids = prompt + [7]
+    cached = NS(req_ids=["p"], new_block_ids=[None], resumed_req_ids=set(), all_token_ids={}, num_computed_tokens=[len(prompt)])
+    assert sched.build_meta(sched_out(cached=cached, num_sched={"p": 1})) == []

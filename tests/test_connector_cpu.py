@@ -309,3 +309,11 @@ def test_layout_detection_on_tensors_built_like_vllms_model_runner(backend, layo
             want = (t[kv, b, j, g, e] if tuple(shape)[0] == 2 else t[b, kv, j, g, e]).data_ptr()
             inner = (g * bs * D + j * D + e) if tile == _lib.LAYOUT_HND else (j * H * D + g * D + e)
             assert base + b * stride + inner * es == want, (backend, layout, kv, b, j, g, e)
+
+
+def test_several_kv_cache_groups_are_refused():
+    from vllm.distributed.kv_transfer.kv_connector.v1.base import KVConnectorRole
+
+    from b200kv.connector import B200KVConnector
+    with pytest.raises(ValueError, match="single KV-cache group"):
+        B200KVConnector(fake_vllm_config("hyb"), KVConnectorRole.SCHEDULER, NS(kv_cache_groups=[object(), object()]))

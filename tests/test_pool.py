@@ -170,7 +170,7 @@ def test_bad_arguments():
 def test_stale_writer_and_stale_pin_are_reclaimed(monkeypatch):
     """A writer that died between reserve and commit, and a reader that died between acquire and
     release, must not wedge the pool: both are recognised by age (B200KV_POOL_STALE_MS)."""
-    monkeypatch.setenv("B200KV_POOL_STALE_MS", "80")
+    monkeypatch.setenv("B200KV_POOL_STALE_MS", "400")
     p = mk(2)
     p.reserve(1, 256)                      # never committed
     put(p, 2)
@@ -179,7 +179,7 @@ def test_stale_writer_and_stale_pin_are_reclaimed(monkeypatch):
         with pytest.raises(B200KVError) as ei:
             p.reserve(key, 256)
         assert ei.value.code == (_lib.EEXIST if key == 1 else _lib.ENOSPC)
-    time.sleep(0.15)
+    time.sleep(0.6)
     put(p, 1, fill=7)                      # the dead writer's key is taken over
     put(p, 3)                              # the dead reader's pin no longer protects chunk 2
     keys = np.array([2], np.uint64)

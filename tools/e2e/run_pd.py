@@ -1,5 +1,6 @@
-"""Disaggregated prefill end to end on 2 B200s (BASELINE.json configs[4] shape, scaled to 1P + 1D):
-a prefill `vllm serve` on GPU 0 and a decode `vllm serve` on GPU 1, both with B200KVConnector, and the
+"""Disaggregated prefill end to end (BASELINE.json configs[4]: `--prefill 4 --decode 4` on 8 B200s; default
+1P + 1D on 2): prefill `vllm serve`s on GPUs 0..P-1 and decode `vllm serve`s on GPUs P..P+D-1, all with
+B200KVConnector, requests paired round-robin like the router does (routing_logic.py:619-641), and the
 two-step flow the unmodified router performs in `route_orchestrated_disaggregated_request`
 (/root/reference/src/vllm_router/services/request_service/request.py:755-908):
 
@@ -64,35 +65,42 @@ async def stream_completion(session, url, body):
     return (first or time.time()) - t0, "".join(text)
 
 
-async def drive(args, p_url, d_url):
+async def drive(args, p_urls, d_urls):
     rows = []
     timeout = aiohttp.ClientTimeout(total=600)
+    sem = asyncio.Semaphore(max(1, args.concurrency))
     async with aiohttp.ClientSession(timeout=timeout) as s:
-        for i in range(args.requests):
-            prompt = f"request {i} " + " ".join(["hi"] * args.prompt_words)
-            base = {"model": "synth-llama3-8b", "prompt": prompt, "max_tokens": args.max_tokens, "temperature": 0}
-            # reference: one engine does everything (decode engine, no hand-off)
-            ref_ttft, ref_text = await stream_completion(s, d_url + "/v1/completions", dict(base, stream=True))
-            # step 1: prefill
-            t0 = time.time()
-            pre = dict(base, max_tokens=1, stream=False,
-                       kv_transfer_params={"do_remote_decode": True, "do_remote_prefill": False, "remote_engine_id": None,
-                                           "remote_block_ids": None, "remote_host": None, "remote_port": None})
-            async with s.post(p_url + "/v1/completions", json=pre) as r:
-                r.raise_for_status()
-                pdata = await r.json()
-            t_prefill = time.time() - t0
-            ktp = pdata.get("kv_transfer_params") or {}
-            if ktp:
-                ktp["remote_host"] = "127.0.0.1"
-            # step 2: decode with the hand-off
-            d_ttft, d_text = await stream_completion(s, d_url + "/v1/completions",
-                                                     dict(base, stream=True, kv_transfer_params=ktp))
-            rows.append({"prefill_s": t_prefill, "decode_ttft_s": d_ttft, "single_engine_ttft_s": ref_ttft,
-                         "handoff_params": bool(ktp), "n_remote_blocks": len((ktp.get("remote_block_ids") or [])),
-                         "same_text": hashlib.sha1(d_text.encode()).hexdigest() == hashlib.sha1(ref_text.encode()).hexdigest(),
-                         "prompt_tokens": pdata.get("usage", {}).get("prompt_tokens")})
+        async def one(i):
+            async with sem:
+                rows.append(await one_request(args, s, i, p_urls[i % len(p_urls)], d_urls[i % len(d_urls)]))
+        await asyncio.gather(*[one(i) for i in range(args.requests)])
     return rows
+
+
+async def one_request(args, s, i, p_url, d_url):
+    prompt = f"request {i} " + " ".join(["hi"] * args.prompt_words)
+    base = {"model": "synth-llama3-8b", "prompt": prompt, "max_tokens": args.max_tokens, "temperature": 0}
+    # reference: one engine does everything (decode engine, no hand-off)
+    ref_ttft, ref_text = await stream_completion(s, d_url + "/v1/completions", dict(base, stream=True))
+    # step 1: prefill
+    t0 = time.time()
+    pre = dict(base, max_tokens=1, stream=False,
+               kv_transfer_params={"do_remote_decode": True, "do_remote_prefill": False, "remote_engine_id": None,
+                                   "remote_block_ids": None, "remote_host": None, "remote_port": None})
+    async with s.post(p_url + "/v1/completions", json=pre) as r:
+        r.raise_for_status()
+        pdata = await r.json()
+    t_prefill = time.time() - t0
+    ktp = pdata.get("kv_transfer_params") or {}
+    if ktp:
+        ktp["remote_host"] = "127.0.0.1"
+    # step 2: decode with the hand-off
+    d_ttft, d_text = await stream_completion(s, d_url + "/v1/completions",
+                                             dict(base, stream=True, kv_transfer_params=ktp))
+    return {"prefill_s": t_prefill, "decode_ttft_s": d_ttft, "single_engine_ttft_s": ref_ttft,
+            "handoff_params": bool(ktp), "n_remote_blocks": len((ktp.get("remote_block_ids") or [])),
+            "same_text": hashlib.sha1(d_text.encode()).hexdigest() == hashlib.sha1(ref_text.encode()).hexdigest(),
+            "prompt_tokens": pdata.get("usage", {}).get("prompt_tokens"), "prefill": p_url, "decode": d_url}
 
 
 def metrics_of(port):
@@ -114,24 +122,40 @@ def main():
     ap.add_argument("--max-model-len", type=int, default=8704)
     ap.add_argument("--max-tokens", type=int, default=64)
     ap.add_argument("--requests", type=int, default=6)
+    ap.add_argument("--prefill", type=int, default=1, help="number of prefill engines (GPUs 0..P-1)")
+    ap.add_argument("--decode", type=int, default=1, help="number of decode engines (GPUs P..P+D-1)")
+    ap.add_argument("--concurrency", type=int, default=1, help="requests in flight")
+    ap.add_argument("--mock", action="store_true", help="orchestration dry run with tools/mock_backend.py (no GPU)")
     ap.add_argument("--extra", default="")
     ap.add_argument("--log-dir", default=os.path.join(ROOT, "gpurun_out"))
     args = ap.parse_args()
     os.makedirs(args.log_dir, exist_ok=True)
-    subprocess.run([sys.executable, os.path.join(HERE, "make_model.py"), args.model_dir, "--layers", str(args.layers),
-                    "--max-len", str(args.max_model_len)], check=True, stdout=subprocess.DEVNULL)
+    if not args.mock:
+        subprocess.run([sys.executable, os.path.join(HERE, "make_model.py"), args.model_dir, "--layers", str(args.layers),
+                        "--max-len", str(args.max_model_len)], check=True, stdout=subprocess.DEVNULL)
     extra = args.extra.split() if args.extra else []
     procs = []
     res = {}
     try:
-        p_proc, p_log = start_server(0, 8021, args.model_dir, args.max_model_len, os.path.join(args.log_dir, "vllm_pd_prefill.log"), extra)
-        d_proc, d_log = start_server(1, 8022, args.model_dir, args.max_model_len, os.path.join(args.log_dir, "vllm_pd_decode.log"), extra)
-        procs = [(p_proc, p_log), (d_proc, d_log)]
-        ok = wait_ready(8021, p_proc, 1200) and wait_ready(8022, d_proc, 1200)
+        n = args.prefill + args.decode
+        ports = [8021 + i for i in range(n)]
+        for i, port in enumerate(ports):
+            kind = "prefill" if i < args.prefill else "decode"
+            log_path = os.path.join(args.log_dir, f"vllm_pd_{kind}{i}.log")
+            if args.mock:
+                log = open(log_path, "w")
+                procs.append((subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "mock_backend.py"), "--port", str(port),
+                                                "--model", "synth-llama3-8b"], stdout=log, stderr=subprocess.STDOUT,
+                                               start_new_session=True), log))
+            else:
+                procs.append(start_server(i, port, args.model_dir, args.max_model_len, log_path, extra))
+        ok = all(wait_ready(port, pr[0], 1200) for port, pr in zip(ports, procs))
+        p_urls = [f"http://127.0.0.1:{p}" for p in ports[:args.prefill]]
+        d_urls = [f"http://127.0.0.1:{p}" for p in ports[args.prefill:]]
         if not ok:
             res["error"] = "servers not ready"
         else:
-            rows = asyncio.run(drive(args, "http://127.0.0.1:8021", "http://127.0.0.1:8022"))
+            rows = asyncio.run(drive(args, p_urls, d_urls))
             time.sleep(2)
             res = {"requests": len(rows), "prompt_tokens": rows[0]["prompt_tokens"],
                    "handoff_params_returned": sum(r["handoff_params"] for r in rows),
@@ -140,7 +164,8 @@ def main():
                    "decode_ttft_p50_ms": statistics.median(r["decode_ttft_s"] for r in rows) * 1e3,
                    "single_engine_ttft_p50_ms": statistics.median(r["single_engine_ttft_s"] for r in rows) * 1e3,
                    "same_text": f"{sum(r['same_text'] for r in rows)}/{len(rows)}",
-                   "rows": rows, "prefill_metrics": metrics_of(8021), "decode_metrics": metrics_of(8022)}
+                   "engines": {"prefill": p_urls, "decode": d_urls}, "concurrency": args.concurrency,
+                   "rows": rows, "prefill_metrics": metrics_of(ports[0]), "decode_metrics": metrics_of(ports[args.prefill])}
     finally:
         for proc, log in procs:
             try:

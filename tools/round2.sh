@@ -36,6 +36,7 @@ case "$stage" in
   scale8)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus 8 > "$out/bench_n8.json" 2> "$out/bench_n8.err"
+    python tools/e2e/run_pd.py --prefill 4 --decode 4 --concurrency 4 --requests 16 --log-dir "$out/pd_4p4d" 2>&1 | cut -c1-500
     python tools/e2e/run_multi.py --replicas 8 --routing session --modes none,shared --num-users 64 --num-rounds 4 --qps 8 \
         --log-dir "$out/multi8_session" 2>&1 | cut -c1-600
     ;;
