@@ -103,10 +103,11 @@ def session_tokens(rank: int, step: int, s: int) -> np.ndarray:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024):
+def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024, target_s: float = 0.0):
     """store+retrieve of `sessions` x 2K-ctx requests per step with oracle/liboracle.so (gather
     into a host chunk buffer = the CPU pool, scatter back into other pages).  Returns
-    (GB/s payload, ms/step, threads, sample description)."""
+    (GB/s payload, ms/step, threads, sample description).  target_s > 0: the number of steps is
+    chosen so the timed sample is about that many seconds of CPU work (bounded to [steps, 4000])."""
     from oracle import kv_oracle as ko
     from tests import oracle_c
     rng = np.random.default_rng(0)
@@ -133,12 +134,17 @@ def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024):
 
     for w in range(warmup):
         one_step(w)
+    if target_s > 0:
+        t0 = time.perf_counter()
+        one_step(warmup)
+        steps = int(min(4000, max(steps, target_s / max(time.perf_counter() - t0, 1e-4))))
     t0 = time.perf_counter()
     for k in range(steps):
         one_step(warmup + k)
     dt = time.perf_counter() - t0
     payload = 2 * sessions * CTX * TOKEN_BYTES_ALL * steps
-    sample = f"{sessions} sessions x {CTX} tokens per step (of {SESSIONS}), paged cache {nb} blocks in host RAM, RAW bf16"
+    sample = (f"{steps} steps x {sessions} sessions x {CTX} tokens (of {SESSIONS} per GPU step), {dt:.1f} s of CPU work, "
+              f"paged cache {nb} blocks in host RAM, RAW bf16")
     return payload / dt / 1e9, dt / steps * 1e3, threads, sample
 
 
@@ -431,7 +437,7 @@ def run_ours(args):
         os.sched_setaffinity(0, range(os.cpu_count()))
     except Exception:
         pass
-    cpu_gbps, cpu_ms, cpu_threads, cpu_sample = cpu_oracle_run(3, 1)
+    cpu_gbps, cpu_ms, cpu_threads, cpu_sample = cpu_oracle_run(3, 1, target_s=10.0)
     line = {
         "metric": "kv_offload_GBps", "value": value_gbps, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
