@@ -58,6 +58,10 @@ extern "C" {
  *        (helm/templates/deployment-vllm-multi.yaml:341-344).                              */
 #define B200KV_FMT_RAW 0
 #define B200KV_FMT_FP8 1
+/* Q4 (experimental): group-wise 4-bit — per (token, head) groups of 32 elements, bf16 scale = absmax/7,
+ * two's-complement nibbles; a stored token of one plane is [H*D/2 codes][H*D/32 scales] (4.5 bits per
+ * element).  Specified by oracle/kv_oracle.py q4_pack_chunk.  Source dtype bf16, D % 32 == 0.        */
+#define B200KV_FMT_Q4 2
 
 /* ---- order inside one (block, K|V) tile of the paged cache ------------------------------ */
 /* NHD: [block_tokens][H][D] (FlashAttention default, vllm/v1/attention/backends/flash_attn.py:
@@ -144,6 +148,11 @@ void* b200kv_pool_slot_ptr(b200kv_pool* pool, uint32_t slot);
 int b200kv_pool_lookup(b200kv_pool* pool, const uint64_t* keys, const int32_t* chunk_tokens,
                        int32_t n_keys, uint32_t lease_ms, int32_t* n_hit_chunks,
                        int64_t* n_hit_tokens);
+/* Per-key membership (not prefix): present[i] = 1 iff keys[i] is READY (and holds chunk_tokens[i]
+ * tokens when chunk_tokens is given).  Present chunks are leased for lease_ms.  Used to combine
+ * several tiers (host pool, device tiers of this and of peer replicas) into one prefix.        */
+int b200kv_pool_contains(b200kv_pool* pool, const uint64_t* keys, const int32_t* chunk_tokens,
+                         int32_t n_keys, uint32_t lease_ms, uint8_t* present);
 /* First instance (owner tag given at reserve time) holding each of the first n_hit chunks;
  * answers the router's LookupMsg (src/vllm_router/routers/routing_logic.py:378-387).       */
 int b200kv_pool_lookup_owner(b200kv_pool* pool, const uint64_t* keys, int32_t n_keys,
@@ -286,6 +295,20 @@ int b200kv_import_peer_ptrs(b200kv_ctx* ctx, int32_t peer_id, int32_t peer_devic
 int b200kv_peer_pull_async(b200kv_ctx* ctx, int32_t peer_id, const int64_t* src_slots,
                            const int64_t* dst_slots, int64_t n_tokens, void* compute_stream,
                            uint64_t* ticket);
+
+/* ---- device chunk tier (BASELINE.json configs[3]: peer-GPU KV pull over NVLink, no host hop) ----- */
+/* gather / scatter with one device pointer PER CHUNK instead of one contiguous buffer: the chunk may
+ * sit in this engine's device tier or in a peer replica's (a pointer into a b200kv_tier_import
+ * mapping: the scatter kernels then read it with P2P loads over NVSwitch).                        */
+int b200kv_gather_chunks(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                         const uint64_t* chunk_ptrs, void* stream);
+int b200kv_scatter_chunks(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                          const uint64_t* chunk_ptrs, void* stream);
+/* A buffer of n_slots chunk-format slots in HBM (slot i at base + i * chunk_bytes).  Which key sits
+ * where, LRU and pins are kept by the caller in a b200kv_pool index in shm, shared with the peers.   */
+int b200kv_tier_create(b200kv_ctx* ctx, uint32_t n_slots, uint64_t* base_out);
+int b200kv_tier_export(b200kv_ctx* ctx, b200kv_ipc_desc* desc_out);
+int b200kv_tier_import(b200kv_ctx* ctx, const b200kv_ipc_desc* desc, uint64_t* mapped_base_out);
 
 int b200kv_engine_get_stats(b200kv_ctx* ctx, b200kv_engine_stats* out);
 /* Milliseconds of the most recent gather / scatter / pull kernel batch, measured with CUDA

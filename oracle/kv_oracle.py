@@ -241,6 +241,56 @@ def fp8_tolerance(x: np.ndarray, scale_per_elem: np.ndarray) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------
+# q4 group-wise chunk codec (SURVEY.md §8f-4 "sub-8-bit codec"; north_star "optional CacheGen
+# token-chunk quantisation").  SPECIFIED HERE FIRST, oracle-only for now: the CUDA kernels follow it.
+#   * group = Q4_GROUP consecutive elements along D of one (token, head)
+#   * scale = bf16_rn(absmax / 7); codes = clamp(rint(x / scale), -7, 7) as two's-complement nibbles,
+#     element 2i in the low nibble of byte i; absmax == 0 -> scale 1, codes 0
+#   * x_hat = bf16_rn(code * scale)        ->  4 + 16/Q4_GROUP = 4.5 bits per element
+# ---------------------------------------------------------------------------------------------
+Q4_GROUP = 32
+
+
+def q4_pack_chunk(chunk_bits: np.ndarray):
+    """(L, 2, n, H, D) bf16 bit patterns -> (codes uint8 (L,2,n,H,D/2), scales uint16 bf16 bits (L,2,n,H,D/G))."""
+    L, two, n, H, D = chunk_bits.shape
+    assert D % Q4_GROUP == 0
+    x = bf16_bits_to_f32(chunk_bits).reshape(L, two, n, H, D // Q4_GROUP, Q4_GROUP)
+    amax = np.abs(x).max(axis=-1)
+    s_bits = np.where(amax == 0, f32_to_bf16_bits_rn(np.float32(1.0)),
+                      f32_to_bf16_bits_rn((amax / np.float32(7.0)).astype(np.float32)))
+    s = bf16_bits_to_f32(s_bits)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = np.clip(np.rint((x / s[..., None]).astype(np.float32)), -7, 7).astype(np.int8)
+    q = q.reshape(L, two, n, H, D)
+    nib = (q & 0xF).astype(np.uint8)
+    codes = (nib[..., 0::2] | (nib[..., 1::2] << 4)).astype(np.uint8)
+    return codes, s_bits.astype(np.uint16)
+
+
+def q4_unpack_chunk(codes: np.ndarray, scale_bits: np.ndarray) -> np.ndarray:
+    L, two, n, H, Dh = codes.shape
+    lo = (codes & 0xF).astype(np.int8)
+    hi = (codes >> 4).astype(np.int8)
+    lo = np.where(lo > 7, lo - 16, lo)
+    hi = np.where(hi > 7, hi - 16, hi)
+    q = np.empty((L, two, n, H, 2 * Dh), dtype=np.float32)
+    q[..., 0::2], q[..., 1::2] = lo, hi
+    s = bf16_bits_to_f32(scale_bits)
+    x = (q.reshape(L, two, n, H, -1, Q4_GROUP) * s[..., None]).astype(np.float32)
+    return f32_to_bf16_bits_rn(x.reshape(L, two, n, H, 2 * Dh))
+
+
+def q4_tolerance(x: np.ndarray) -> np.ndarray:
+    """|x - x_hat| <= scale/2 + 2^-8 |x| with scale <= absmax_group/7 * (1 + 2^-8): half a quantisation
+    step of the group plus the bf16 roundings of scale and result."""
+    L, two, n, H, D = x.shape
+    amax = np.abs(x.reshape(L, two, n, H, D // Q4_GROUP, Q4_GROUP)).max(axis=-1, keepdims=True)
+    step = np.broadcast_to(amax / 7.0 * (1 + 2.0 ** -7), (L, two, n, H, D // Q4_GROUP, Q4_GROUP)).reshape(x.shape)
+    return step / 2 + np.abs(x) * 2.0 ** -7
+
+
+# ---------------------------------------------------------------------------------------------
 # engine semantics (store / retrieve / lookup as the adapter drives them)
 # ---------------------------------------------------------------------------------------------
 class OracleEngine:
@@ -288,6 +338,8 @@ class OracleEngine:
             bits = gather_tokens(kv_layers, np.asarray(slot_mapping[s:e]))
             if self.fmt == "fp8":
                 payload = fp8_pack_chunk(bits)
+            elif self.fmt == "q4":
+                payload = q4_pack_chunk(bits)
             else:
                 payload = (bits.copy(),)
             if self.capacity is not None and len(self.pool) >= self.capacity:
@@ -310,7 +362,8 @@ class OracleEngine:
             if ent is None or ent[0] != e - s:
                 break
             self._touch(keys[c])
-            bits = fp8_unpack_chunk(ent[1], ent[2]) if self.fmt == "fp8" else ent[1]
+            bits = (fp8_unpack_chunk(ent[1], ent[2]) if self.fmt == "fp8"
+                    else q4_unpack_chunk(ent[1], ent[2]) if self.fmt == "q4" else ent[1])
             scatter_tokens(kv_layers, bits, np.asarray(slot_mapping[s:e]))
             ret[s:e] = True
         return ret

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200kv.so")
 
-FMT_RAW, FMT_FP8 = 0, 1
+FMT_RAW, FMT_FP8, FMT_Q4 = 0, 1, 2   # FMT_Q4: experimental (group-wise 4-bit)
 VARIANT_BULK, VARIANT_LDG = 0, 1
 LAYOUT_NHD, LAYOUT_HND = 0, 1
 POOL_CREATE, POOL_ATTACH, POOL_CREATE_OR_ATTACH = 1, 2, 3
@@ -77,6 +77,7 @@ SIGNATURES = {
     "b200kv_pool_region": (C.c_int, [_P, C.POINTER(_P), _U64P]),
     "b200kv_pool_slot_ptr": (_P, [_P, C.c_uint32]),
     "b200kv_pool_lookup": (C.c_int, [_P, _U64P, _I32P, C.c_int32, C.c_uint32, _I32P, _I64P]),
+    "b200kv_pool_contains": (C.c_int, [_P, _U64P, _I32P, C.c_int32, C.c_uint32, C.POINTER(C.c_uint8)]),
     "b200kv_pool_lookup_owner": (C.c_int, [_P, _U64P, C.c_int32, _I32P, _U32P]),
     "b200kv_pool_reserve": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_uint32, C.c_uint32, _U32P]),
     "b200kv_pool_commit": (C.c_int, [_P, C.c_uint64]),
@@ -103,6 +104,11 @@ SIGNATURES = {
     "b200kv_import_peer": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(IpcDesc), C.c_int32, C.c_uint64, C.c_uint64]),
     "b200kv_import_peer_ptrs": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_P), C.c_uint64, C.c_uint64]),
     "b200kv_peer_pull_async": (C.c_int, [_P, C.c_int32, _I64P, _I64P, C.c_int64, _P, _U64P]),
+    "b200kv_gather_chunks": (C.c_int, [_P, _I64P, C.c_int64, _U64P, _P]),
+    "b200kv_scatter_chunks": (C.c_int, [_P, _I64P, C.c_int64, _U64P, _P]),
+    "b200kv_tier_create": (C.c_int, [_P, C.c_uint32, _U64P]),
+    "b200kv_tier_export": (C.c_int, [_P, C.POINTER(IpcDesc)]),
+    "b200kv_tier_import": (C.c_int, [_P, C.POINTER(IpcDesc), _U64P]),
     "b200kv_engine_get_stats": (C.c_int, [_P, C.POINTER(EngineStats)]),
     "b200kv_last_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "b200kv_server_start": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_P)]),

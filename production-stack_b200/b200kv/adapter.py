@@ -255,6 +255,8 @@ class WorkerStats:
     num_loaded_tokens: int = 0
     num_load_shortfalls: int = 0
     num_foreign_loaded_tokens: int = 0   # loaded from chunks another replica stored (shared pool)
+    num_tier_local_tokens: int = 0       # loaded from this engine's device tier (no PCIe)
+    num_tier_peer_tokens: int = 0        # loaded from a peer replica's device tier (NVLink, no host hop)
     retrieve_seconds: float = 0.0
     retrieve_calls: int = 0
 
@@ -274,6 +276,11 @@ class WorkerState:
         # layer-wise loads of the current step: (ticket, blocks it fills); the forward pass waits per layer
         self.layer_loads: list[tuple[int, list[int]]] = []
         self.on_stored = None    # callable(chunk keys) after a store was issued (remote tier upload)
+        # device chunk tier (b200kv/device_tier.py): this engine's tier, and every tier it can read
+        self.local_tier = None
+        self.tiers = None
+        self._tier_pins: list[tuple[object, list]] = []   # (event after the scatter, [(view, key)]) still pinned
+        self.event_factory = None   # stream -> object with .query(); default torch.cuda.Event (tests inject one)
         self.stats = WorkerStats()
 
     def start_load(self, metas: list[ReqMeta], stream=None, layers_per_group: int = 0):
@@ -296,7 +303,12 @@ class WorkerState:
             mask[:masked] = False
             t0 = time.perf_counter()
             try:
-                if m.async_load:
+                ret = None
+                if self.tiers is not None and not m.async_load:
+                    ret = self._load_with_tiers(tokens, sm, masked, stream)   # None: no tier holds any of it
+                if ret is not None:
+                    pass
+                elif m.async_load:
                     ret, ticket = self.engine.retrieve(tokens, mask, sm, stream="detached", return_ticket=True)
                     self.async_loads.append((ticket, m.req_id))
                 elif layers_per_group > 0:
@@ -325,6 +337,67 @@ class WorkerState:
                 first_bad = (masked + got) // self.block_size
                 last = (n + self.block_size - 1) // self.block_size
                 self.load_error_blocks.update(m.block_ids[first_bad:last])
+
+    def _load_with_tiers(self, tokens, sm, masked: int, stream) -> np.ndarray:
+        """Chunk by chunk from the nearest copy: a device tier (own, then a peer's: scatter straight from
+        HBM / over NVLink) or the pinned host pool (engine.retrieve).  The loaded tokens form a prefix of
+        [masked, n), like the host path."""
+        n, C_ = len(tokens), self.chunk
+        keys = self.engine._keys(tokens)
+        ct = np.minimum(C_, n - np.arange(len(keys)) * C_).astype(np.int32)
+        c0 = masked // C_
+        self.tiers.refresh()
+        src = self.tiers.resolve(keys[c0:], ct[c0:])      # pins what it finds
+        if all(s_ is None for s_ in src):
+            return None                                   # the ordinary host path (layer-wise etc.) applies
+        ret = np.zeros(n, dtype=bool)
+        pins, c, n_chunks = [], c0, len(keys)
+        try:
+            while c < n_chunks:
+                e = c
+                if src[c - c0] is not None:
+                    while e < n_chunks and src[e - c0] is not None:
+                        e += 1
+                    end = min(e * C_, n)
+                    ptrs = [v.base + slot * v.chunk_bytes for v, slot in src[c - c0:e - c0]]
+                    self.engine.scatter_chunks(sm[c * C_:end], ptrs, stream)
+                    for i in range(c, e):
+                        v = src[i - c0][0]
+                        pins.append((v, int(keys[i])))
+                        if v.local:
+                            self.stats.num_tier_local_tokens += int(ct[i])
+                        else:
+                            self.stats.num_tier_peer_tokens += int(ct[i])
+                    ret[c * C_:end] = True
+                else:
+                    while e < n_chunks and src[e - c0] is None:
+                        e += 1
+                    end = min(e * C_, n)
+                    m2 = np.ones(end, dtype=bool)
+                    m2[:c * C_] = False
+                    got = int(np.asarray(self.engine.retrieve(tokens[:end], m2, sm[:end], stream=stream)).sum())
+                    ret[c * C_:c * C_ + got] = True
+                    if got < end - c * C_:
+                        break                 # the prefix ends here; later tier pins are dropped below
+                c = e
+        finally:
+            used = {(id(v), k) for v, k in pins}
+            unused = [(s_[0], int(keys[c0 + i])) for i, s_ in enumerate(src)
+                      if s_ is not None and (id(s_[0]), int(keys[c0 + i])) not in used]
+            self.tiers.release(unused)
+            if pins:
+                self._tier_pins.append((self._tier_event(stream), pins))
+        return ret
+
+    def _tier_event(self, stream):
+        if self.event_factory is not None:
+            return self.event_factory(stream)
+        if self.local_tier is not None:
+            return self.local_tier._event(stream)
+        import torch
+        ev = torch.cuda.Event()
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        return ev
 
     def _foreign_tokens(self, tokens, lo: int, hi: int) -> int:
         """Tokens of [lo, hi) that sit in chunks first stored by ANOTHER instance of a shared pool
@@ -371,6 +444,14 @@ class WorkerState:
                     self.on_stored(self.engine._keys(tokens[:n])[lead // self.chunk:])
                 except Exception as e:
                     logger.error("b200kv: remote upload hook failed for %s: %s", m.req_id, e)
+            if self.local_tier is not None:
+                try:
+                    c0 = lead // self.chunk
+                    keys = self.engine._keys(tokens[:n])[c0:]
+                    ct = np.minimum(self.chunk, n - (c0 + np.arange(len(keys))) * self.chunk).astype(np.int32)
+                    self.local_tier.put(keys, ct, sm[lead:], self.chunk, stream)
+                except Exception as e:
+                    logger.error("b200kv: device tier store failed for %s: %s", m.req_id, e)
             ss.skip_leading_tokens = n
 
     def wait_layer(self, layer: int, stream=None):
@@ -386,6 +467,16 @@ class WorkerState:
 
     def reap(self):
         self.pending_tickets = [t for t in self.pending_tickets if not self.engine.poll(t)]
+        if self.local_tier is not None:
+            self.local_tier.poll()
+        if self._tier_pins:
+            still = []
+            for ev, pins in self._tier_pins:
+                if ev.query():
+                    self.tiers.release(pins)
+                else:
+                    still.append((ev, pins))
+            self._tier_pins = still
 
     def poll_async_loads(self) -> set[str]:
         """Request ids whose detached load has landed (finished_recving of get_finished)."""

@@ -9,7 +9,7 @@ import logging
 import os
 from dataclasses import dataclass, field
 
-from ._lib import FMT_FP8, FMT_RAW
+from ._lib import FMT_FP8, FMT_Q4, FMT_RAW
 
 logger = logging.getLogger("b200kv")
 
@@ -50,6 +50,7 @@ class B200KVConfig:
     layerwise: bool = True                # B200KV_LAYERWISE / LMCACHE_USE_LAYERWISE: per-layer-group loads (default on:
                                           # TTFT 24.4 -> 19.3 ms, outputs identical; profiles/e2e_mrqa_r01.json)
     layer_group: int = 4                  # B200KV_LAYER_GROUP: layers per group
+    device_tier_gb: float = 0.0           # B200KV_DEVICE_TIER_GB: HBM kept as a chunk cache peers can pull from (0 = off)
     remote_url: str | None = None         # LMCACHE_REMOTE_URL=lm://host:port: cache-server tier (b200kv/remote.py)
     remote_wait_ms: int = 2000            # B200KV_REMOTE_WAIT_MS: longest a request waits for its remote prefetch
     extra: dict = field(default_factory=dict)
@@ -75,9 +76,9 @@ class B200KVConfig:
         c.max_local_cpu_size_gb = float(e.get("LMCACHE_MAX_LOCAL_CPU_SIZE", c.max_local_cpu_size_gb))
         serde = (e.get("LMCACHE_REMOTE_SERDE") or "").lower()
         fmt = (e.get("B200KV_FORMAT") or ("fp8" if serde == "cachegen" else "raw")).lower()
-        if fmt not in ("raw", "bf16", "naive", "fp8"):
-            raise ValueError(f"B200KV_FORMAT={fmt!r}: expected raw|fp8")
-        c.fmt = FMT_FP8 if fmt == "fp8" else FMT_RAW
+        if fmt not in ("raw", "bf16", "naive", "fp8", "q4"):
+            raise ValueError(f"B200KV_FORMAT={fmt!r}: expected raw|fp8|q4")
+        c.fmt = {"fp8": FMT_FP8, "q4": FMT_Q4}.get(fmt, FMT_RAW)
         c.save_unfull_chunk = _b(e.get("LMCACHE_SAVE_UNFULL_CHUNK"), True)
         c.save_decode_cache = _b(e.get("LMCACHE_SAVE_DECODE_CACHE"), False)
         c.priority_limit = int(e["LMCACHE_PRIORITY_LIMIT"]) if e.get("LMCACHE_PRIORITY_LIMIT") not in (None, "") else None
@@ -94,6 +95,7 @@ class B200KVConfig:
         c.async_load = _b(e.get("B200KV_ASYNC_LOAD"), False)
         c.layerwise = _b(e.get("B200KV_LAYERWISE", e.get("LMCACHE_USE_LAYERWISE")), True)
         c.layer_group = max(1, int(e.get("B200KV_LAYER_GROUP", c.layer_group)))
+        c.device_tier_gb = float(e.get("B200KV_DEVICE_TIER_GB", c.device_tier_gb))
         c.remote_url = e.get("LMCACHE_REMOTE_URL") or None
         c.remote_wait_ms = int(e.get("B200KV_REMOTE_WAIT_MS", c.remote_wait_ms))
         for k in _IGNORED:
@@ -112,7 +114,7 @@ class B200KVConfig:
                 if k.startswith(prefix):
                     name = k[len(prefix):]
                     if name == "format":
-                        self.fmt = FMT_FP8 if str(v).lower() == "fp8" else FMT_RAW
+                        self.fmt = {"fp8": FMT_FP8, "q4": FMT_Q4}.get(str(v).lower(), FMT_RAW)
                     elif hasattr(self, name):
                         cur = getattr(self, name)
                         setattr(self, name, type(cur)(v) if cur is not None and not isinstance(cur, bool)

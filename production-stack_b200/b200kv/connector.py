@@ -145,8 +145,23 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             pool = self._pool
             include_partial = not self._discard_partial
 
+            self._tiers = None
+            if self.cfg.device_tier_gb > 0:      # index-only view of every replica's device tier
+                from .device_tier import TierSet
+                self._tiers = TierSet(self._engine_id, geom.chunk_bytes, None)
+            tiers = self._tiers
+
             def lookup(token_ids):
-                return pool.lookup_tokens(token_ids, chunk, seed, lease, include_partial)
+                if tiers is None:
+                    return pool.lookup_tokens(token_ids, chunk, seed, lease, include_partial)
+                from .device_tier import combined_prefix_tokens
+                from .engine import chunk_keys
+                import numpy as np
+                toks = np.asarray(token_ids, dtype=np.int32)
+                keys = chunk_keys(toks, chunk, seed, include_partial)
+                ct = np.minimum(chunk, len(toks) - np.arange(len(keys)) * chunk).astype(np.int32)
+                tiers.refresh()
+                return combined_prefix_tokens(pool, tiers, keys, ct, lease)
 
             self._sched = SchedulerState(lookup, self._block_size, self._chunk, self._discard_partial,
                                          self.cfg.save_decode_cache, self.kv_role, async_load=self.cfg.async_load,
@@ -160,7 +175,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                 atexit.register(KVPool.unlink, self._pool_name)
         logger.info("b200kv connector role=%s kv_role=%s pool=%s (%.1f GB, chunk %d, fmt %s)",
                     role.name, self.kv_role, self._pool_name, self.cfg.max_local_cpu_size_gb, self._chunk,
-                    "fp8" if self.cfg.fmt else "raw")
+                    ("raw", "fp8", "q4")[self.cfg.fmt])
 
     def _make_remote(self, key_seeds):
         """LMCACHE_REMOTE_URL=lm://host:port (deployment-vllm-multi.yaml:338-345): the cache-server
@@ -212,6 +227,20 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._layer_hooks_seen = 0
         self._worker = WorkerState(self._engine, self._block_size, self._chunk, self.kv_role,
                                    owner_tag=owner_tag_of(self.cfg.instance_id) if self.cfg.pool_name else 0)
+        if self.cfg.device_tier_gb > 0:
+            from .device_tier import LocalTier, TierSet
+            fmt_tag = self.cfg.fmt | (tile_layout << 8)
+            try:
+                n_slots = max(1, int(self.cfg.device_tier_gb * (1 << 30)) // geom.chunk_bytes)
+                self._worker.tiers = TierSet(self._engine_id, geom.chunk_bytes, fmt_tag, importer=self._engine.tier_import)
+                if self.kv_role != "kv_consumer":
+                    self._worker.local_tier = LocalTier(self._engine, self._engine_id, n_slots, t0.device.index or 0,
+                                                        fmt_tag, owner_tag_of(self.cfg.instance_id))
+                    self._worker.tiers.add_local(self._worker.local_tier)
+                logger.info("b200kv device tier: %d chunk slots in HBM", n_slots)
+            except Exception as e:
+                logger.warning("b200kv: device tier unavailable (%s)", e)
+                self._worker.tiers = self._worker.local_tier = None
         if self.kv_role != "kv_consumer":
             self._remote = self._make_remote(self._engine.key_seed)
             if self._remote is not None:
@@ -313,6 +342,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         cur = {"num_stored_tokens": ws.num_stored_tokens, "num_loaded_tokens": ws.num_loaded_tokens,
                "retrieve_seconds": ws.retrieve_seconds, "retrieve_calls": ws.retrieve_calls,
                "load_shortfalls": ws.num_load_shortfalls, "num_foreign_loaded_tokens": ws.num_foreign_loaded_tokens,
+               "num_tier_local_tokens": ws.num_tier_local_tokens, "num_tier_peer_tokens": ws.num_tier_peer_tokens,
                # the scheduler's counters are per engine, not per TP rank: rank 0 reports them
                "num_hit_tokens": self._sched_counters[1] if getattr(self, "_rank", 0) == 0 else 0,
                "num_requested_tokens": self._sched_counters[2] if getattr(self, "_rank", 0) == 0 else 0,
@@ -347,6 +377,14 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         if self._pdw is not None:
             unpublish_ipc(self._engine_id)
             self._pdw = None
+        if self._worker is not None and self._worker.tiers is not None:
+            if self._worker.local_tier is not None:
+                self._worker.local_tier.close()
+            self._worker.tiers.close()
+            self._worker.tiers = self._worker.local_tier = None
+        if getattr(self, "_tiers", None) is not None:
+            self._tiers.close()
+            self._tiers = None
         if self._engine is not None:
             self._engine.wait_all()
             self._engine.close()

@@ -104,7 +104,11 @@ class KVGeometry:
     def payload_bytes_per_token(self) -> int:
         """Bytes one token occupies in a stored chunk (SURVEY.md §8d 'payload P')."""
         per = 2 * self.n_layers * self.token_bytes
-        return per if self.fmt == FMT_RAW else per // 2
+        if self.fmt == FMT_RAW:
+            return per
+        if self.fmt == FMT_FP8:
+            return per // 2
+        return per * 9 // 32          # Q4: 4 bits + one bf16 scale per 32 elements = 4.5 bits per element
 
 
 class KVPool:
@@ -142,6 +146,16 @@ class KVPool:
             return 0
         ct = np.minimum(chunk_tokens, len(toks) - np.arange(len(keys)) * chunk_tokens).astype(np.int32)
         return self.lookup(keys, ct, lease_ms)[1]
+
+    def contains(self, keys, chunk_tokens=None, lease_ms: int = 0) -> np.ndarray:
+        """Per-key membership (bool array), leasing what is present (b200kv_pool_contains)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(len(keys), dtype=np.uint8)
+        ct = None if chunk_tokens is None else np.ascontiguousarray(chunk_tokens, dtype=np.int32)
+        check(lib().b200kv_pool_contains(self.handle, _ptr(keys, C.c_uint64), None if ct is None else _ptr(ct, C.c_int32),
+                                         len(keys), lease_ms, out.ctypes.data_as(C.POINTER(C.c_uint8))),
+              "b200kv_pool_contains")
+        return out.astype(bool)
 
     def lookup_owner(self, keys: np.ndarray) -> tuple[int, np.ndarray]:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -371,6 +385,35 @@ class KVEngine:
                                     _stream_ptr(stream)), "b200kv_scatter")
 
     # ---- peers ----------------------------------------------------------------------------
+    # ---- device chunk tier --------------------------------------------------------------------
+    def tier_create(self, n_slots: int) -> int:
+        base = C.c_uint64(0)
+        check(lib().b200kv_tier_create(self._h, n_slots, C.byref(base)), "b200kv_tier_create")
+        return base.value
+
+    def tier_export(self) -> bytes:
+        d = _lib.IpcDesc()
+        check(lib().b200kv_tier_export(self._h, C.byref(d)), "b200kv_tier_export")
+        return bytes(d)
+
+    def tier_import(self, desc: bytes) -> int:
+        d = _lib.IpcDesc.from_buffer_copy(desc)
+        base = C.c_uint64(0)
+        check(lib().b200kv_tier_import(self._h, C.byref(d), C.byref(base)), "b200kv_tier_import")
+        return base.value
+
+    def gather_chunks(self, slot_mapping, chunk_ptrs, stream=None):
+        sm = _as_i64(slot_mapping)
+        ptrs = np.ascontiguousarray(chunk_ptrs, dtype=np.uint64)
+        check(lib().b200kv_gather_chunks(self._h, _ptr(sm, C.c_int64), len(sm), _ptr(ptrs, C.c_uint64),
+                                         _stream_ptr(stream)), "b200kv_gather_chunks")
+
+    def scatter_chunks(self, slot_mapping, chunk_ptrs, stream=None):
+        sm = _as_i64(slot_mapping)
+        ptrs = np.ascontiguousarray(chunk_ptrs, dtype=np.uint64)
+        check(lib().b200kv_scatter_chunks(self._h, _ptr(sm, C.c_int64), len(sm), _ptr(ptrs, C.c_uint64),
+                                          _stream_ptr(stream)), "b200kv_scatter_chunks")
+
     def export_ipc(self) -> bytes:
         n = 2 * self.geom.n_layers
         arr = (_lib.IpcDesc * n)()

@@ -15,7 +15,7 @@ from vllm.distributed.kv_transfer.kv_connector.v1.metrics import KVConnectorProm
 
 _SUM_KEYS = ("num_hit_tokens", "num_requested_tokens", "num_stored_tokens", "num_loaded_tokens",
              "retrieve_seconds", "retrieve_calls", "retrieve_bytes", "store_bytes", "load_shortfalls",
-             "num_foreign_loaded_tokens")
+             "num_foreign_loaded_tokens", "num_tier_local_tokens", "num_tier_peer_tokens")
 
 
 @dataclass
@@ -37,7 +37,8 @@ class B200KVStats(KVConnectorStats):
     def reduce(self) -> dict[str, int | float]:
         d = self.data
         out: dict[str, int | float] = {k: d[k] for k in ("num_hit_tokens", "num_requested_tokens", "num_stored_tokens",
-                                                          "num_loaded_tokens", "num_foreign_loaded_tokens") if k in d}
+                                                          "num_loaded_tokens", "num_foreign_loaded_tokens", "num_tier_local_tokens",
+                                                          "num_tier_peer_tokens") if k in d}
         if d.get("retrieve_seconds"):
             out["retrieve_GBps"] = round(d.get("retrieve_bytes", 0) / d["retrieve_seconds"] / 1e9, 2)
         if "local_cache_usage_bytes" in d:
@@ -65,6 +66,12 @@ class B200KVPromMetrics(KVConnectorPromMetrics):
         self.foreign = per_engine(c(name="b200kv:cross_replica_loaded_tokens",
                                     documentation="tokens loaded from chunks another replica stored (shared pool)",
                                     labelnames=labelnames))
+        self.tier_local = per_engine(c(name="b200kv:device_tier_local_tokens",
+                                       documentation="tokens loaded from this engine's device chunk tier (no PCIe)",
+                                       labelnames=labelnames))
+        self.tier_peer = per_engine(c(name="b200kv:device_tier_peer_tokens",
+                                      documentation="tokens loaded from a peer replica's device chunk tier over NVLink",
+                                      labelnames=labelnames))
         self.usage = per_engine(g(name="lmcache:local_cache_usage", documentation="bytes of pinned host pool in use",
                                   labelnames=labelnames, multiprocess_mode="mostrecent"))
         self.r_sum = per_engine(c(name="lmcache:retrieve_speed_sum", documentation="sum of retrieve speeds (tokens/s)",
@@ -78,6 +85,8 @@ class B200KVPromMetrics(KVConnectorPromMetrics):
         self.req[engine_idx].inc(d.get("num_requested_tokens", 0))
         self.stored[engine_idx].inc(d.get("num_stored_tokens", 0))
         self.foreign[engine_idx].inc(d.get("num_foreign_loaded_tokens", 0))
+        self.tier_local[engine_idx].inc(d.get("num_tier_local_tokens", 0))
+        self.tier_peer[engine_idx].inc(d.get("num_tier_peer_tokens", 0))
         if "local_cache_usage_bytes" in d:
             self.usage[engine_idx].set(d["local_cache_usage_bytes"])
         if d.get("retrieve_calls") and d.get("retrieve_seconds"):

@@ -150,6 +150,13 @@ int make_geometry(const b200kv_engine_config* c, Geometry* g) {
     g->scales_off = g->slab_bytes * g->planes;
     g->chunk_bytes = g->scales_off + static_cast<uint64_t>(g->planes) * g->H * sizeof(float);
     g->chunk_bytes = (g->chunk_bytes + 255) / 256 * 256;
+  } else if (c->format == B200KV_FMT_Q4) {
+    if (g->elem != 2) return B200KV_ENOTSUP;
+    if (g->D % 32) return B200KV_EINVAL;
+    g->fmt_token_bytes = g->H * g->D / 2 + g->H * (g->D / 32) * 2;   // one token record of one plane
+    g->slab_bytes = static_cast<uint64_t>(g->C) * g->fmt_token_bytes;
+    g->scales_off = 0;
+    g->chunk_bytes = (g->slab_bytes * g->planes + 255) / 256 * 256;
   } else {
     return B200KV_EINVAL;
   }
@@ -197,7 +204,12 @@ struct b200kv_ctx {
   // bulk-kernel launch shape
   int S = 2, LAG = 1, ctas_per_sm = 1;  // swept on B200: profiles/sweep_r01.txt
   int fp8_threads = 256;                // B200KV_FP8_THREADS: CTA width of the FP8 store kernel
+  bool fp8_two_pass = false;            // B200KV_FP8_2PASS=1: smem-free two-pass store kernel (experimental)
   uint32_t piece_tokens = 0, pieces = 0, stage_bytes = 0;
+
+  void* tier_base = nullptr;            // device chunk tier (b200kv_tier_create)
+  uint32_t tier_slots = 0;
+  std::vector<void*> tier_imports;      // peers' tiers opened over CUDA IPC
 };
 
 namespace {
@@ -489,7 +501,8 @@ int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView&
     CU_TRY(cudaFuncSetAttribute(kv_fp8_store_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev] = true;
   }
-  if (ctx->fp8_threads == 512) kv_fp8_store_kernel<512><<<grid, 512, smem, s>>>(p);
+  if (ctx->fp8_two_pass && ctx->g.C / kCluster <= static_cast<uint32_t>(kMaxWindow)) kv_fp8_store2_kernel<<<grid, 256, 0, s>>>(p);
+  else if (ctx->fp8_threads == 512) kv_fp8_store_kernel<512><<<grid, 512, smem, s>>>(p);
   else kv_fp8_store_kernel<256><<<grid, 256, smem, s>>>(p);
   CU_TRY(cudaGetLastError());
   ++ctx->stats.n_kernel_launches;
@@ -524,6 +537,31 @@ int launch_fp8_load(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& 
 }
 
 // chunk-side copy between staging and the pinned pool; partial chunks move only their tokens.
+int launch_q4(b200kv_ctx* ctx, bool store, const uint8_t* dev_table, const TableView& tv, size_t run_begin,
+              size_t n_runs, cudaStream_t s, uint32_t plane_begin = 0, uint32_t n_planes = 0) {
+  Q4Params p{};
+  p.paged = local_side(ctx);
+  p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off) + run_begin;
+  p.chunk_addrs = reinterpret_cast<const uint64_t*>(dev_table + tv.addrs_off);
+  p.n_runs = static_cast<uint32_t>(n_runs);
+  p.n_planes = n_planes ? n_planes : ctx->g.planes;
+  p.plane_begin = plane_begin;
+  p.chunk_tokens = ctx->g.C;
+  p.n_heads = ctx->g.H;
+  p.head_bytes = ctx->g.D * 2;
+  p.slab_bytes = ctx->g.slab_bytes;
+  p.rec_bytes = ctx->g.fmt_token_bytes;
+  p.hnd = ctx->g.hnd ? 1u : 0u;
+  p.total_units = p.n_runs * p.n_planes;
+  const uint32_t grid = std::min<uint32_t>(p.total_units, static_cast<uint32_t>(ctx->sm_count) * 8u);
+  if (grid == 0) return B200KV_OK;
+  if (store) kv_q4_store_kernel<<<grid, 256, 0, s>>>(p);
+  else kv_q4_load_kernel<<<grid, 256, 0, s>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++ctx->stats.n_kernel_launches;
+  return B200KV_OK;
+}
+
 int copy_chunk(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, cudaMemcpyKind kind,
                cudaStream_t s) {
   const Geometry& g = ctx->g;
@@ -533,7 +571,7 @@ int copy_chunk(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_tok, cuda
     moved = g.chunk_bytes;
   } else {
     // HND keeps whole tiles: a ragged tail still occupies its last tile across all heads
-    const uint32_t tok_span = g.hnd ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
+    const uint32_t tok_span = (g.hnd && ctx->cfg.format != B200KV_FMT_Q4) ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
     const size_t width = static_cast<size_t>(tok_span) * g.fmt_token_bytes;
     CU_TRY(cudaMemcpy2DAsync(dst, g.slab_bytes, src, g.slab_bytes, width, g.planes, kind, s));
     moved = width * g.planes;
@@ -561,7 +599,7 @@ int copy_chunk_planes(b200kv_ctx* ctx, void* dst, const void* src, uint32_t n_to
     moved = static_cast<uint64_t>(np) * g.slab_bytes;
     CU_TRY(cudaMemcpyAsync(d, sp, moved, kind, s));
   } else {
-    const uint32_t tok_span = g.hnd ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
+    const uint32_t tok_span = (g.hnd && ctx->cfg.format != B200KV_FMT_Q4) ? (n_tok + g.bs - 1) / g.bs * g.bs : n_tok;
     const size_t width = static_cast<size_t>(tok_span) * g.fmt_token_bytes;
     CU_TRY(cudaMemcpy2DAsync(d, g.slab_bytes, sp, g.slab_bytes, width, np, kind, s));
     moved = width * np;
@@ -680,6 +718,7 @@ static int engine_create_impl(const b200kv_engine_config* cfg, b200kv_pool* pool
   ctx->LAG = env_int("B200KV_LAG", ctx->S / 2);
   ctx->ctas_per_sm = cfg->ctas_per_sm > 0 ? cfg->ctas_per_sm : env_int("B200KV_CTAS_PER_SM", 1);
   ctx->fp8_threads = env_int("B200KV_FP8_THREADS", 256) == 512 ? 512 : 256;
+  ctx->fp8_two_pass = env_int("B200KV_FP8_2PASS", 0) != 0;
   const uint32_t stage_max = static_cast<uint32_t>(env_int("B200KV_STAGE_KB", 32)) << 10;
   if (g.token_bytes > stage_max || stage_max > kStageMax * 2) return B200KV_ENOTSUP;
   ctx->piece_tokens = std::min<uint32_t>(g.bs, stage_max / g.token_bytes);
@@ -770,6 +809,8 @@ extern "C" int b200kv_engine_destroy(b200kv_ctx* ctx) {
       cudaEventDestroy(e.second);
     }
   if (ctx->d_staging) cudaFree(ctx->d_staging);
+  for (void* m : ctx->tier_imports) cudaIpcCloseMemHandle(m);
+  if (ctx->tier_base) cudaFree(ctx->tier_base);
   if (ctx->d_bases) cudaFree(ctx->d_bases);
   for (cudaStream_t s : {ctx->s_gather, ctx->s_d2h, ctx->s_h2d, ctx->s_scatter})
     if (s) cudaStreamDestroy(s);
@@ -801,10 +842,15 @@ extern "C" int b200kv_register_kv(b200kv_ctx* ctx, const void* const* k_ptrs,
 // device-resident gather / scatter
 // ------------------------------------------------------------------------------------------------
 static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_tokens, void* dev_chunks,
-                          void* stream, bool is_gather) {
-  if (!ctx || !slots || n_tokens <= 0 || !dev_chunks) return B200KV_EINVAL;
+                          void* stream, bool is_gather, const uint64_t* chunk_ptrs = nullptr) {
+  if (!ctx || !slots || n_tokens <= 0 || (!dev_chunks && !chunk_ptrs)) return B200KV_EINVAL;
   if (!ctx->kv_registered) return B200KV_EINVAL;
   if (reinterpret_cast<uint64_t>(dev_chunks) % 16) return B200KV_EINVAL;
+  if (chunk_ptrs) {
+    const int64_t n = (n_tokens + ctx->g.C - 1) / ctx->g.C;
+    for (int64_t c = 0; c < n; ++c)
+      if (!chunk_ptrs[c] || chunk_ptrs[c] % 16) return B200KV_EINVAL;
+  }
   DeviceGuard dg(ctx->cfg.device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   const Geometry& g = ctx->g;
@@ -812,7 +858,7 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   const uint32_t n_chunks = static_cast<uint32_t>((n_tokens + g.C - 1) / g.C);
 
   std::vector<Run> runs, partial;
-  const bool fp8 = ctx->cfg.format == B200KV_FMT_FP8;
+  const bool fp8 = ctx->cfg.format != B200KV_FMT_RAW;   // one sorted run list for every transformed format
   int rc = build_runs(ctx, slots, 0, n_tokens, 0, &runs, fp8 ? nullptr : &partial);
   if (rc) return rc;
   const size_t n_full = runs.size(), n_part = partial.size();
@@ -825,7 +871,8 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   uint32_t* offs = reinterpret_cast<uint32_t*>(tv.slot->host + tv.offs_off);
   size_t r = 0;
   for (uint32_t c = 0; c < n_chunks; ++c) {
-    addrs[c] = reinterpret_cast<uint64_t>(dev_chunks) + static_cast<uint64_t>(c) * g.chunk_bytes;
+    addrs[c] = chunk_ptrs ? chunk_ptrs[c]
+                          : reinterpret_cast<uint64_t>(dev_chunks) + static_cast<uint64_t>(c) * g.chunk_bytes;
     offs[c] = static_cast<uint32_t>(r);
     while (r < runs.size() && static_cast<uint32_t>(runs[r].b) / g.C == c) ++r;
   }
@@ -840,6 +887,8 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   if (ctx->cfg.format == B200KV_FMT_FP8) {
     rc = is_gather ? launch_fp8_store(ctx, tv.slot->dev, tv, n_chunks, static_cast<uint32_t>(n_tokens), s)
                    : launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), s);
+  } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+    rc = launch_q4(ctx, is_gather, tv.slot->dev, tv, 0, runs.size(), s);
   } else {
     rc = is_gather ? launch_copy_runs<kStore>(ctx, tv.slot->dev, tv, 0, n_full, n_part, s)
                    : launch_copy_runs<kLoad>(ctx, tv.slot->dev, tv, 0, n_full, n_part, s);
@@ -860,6 +909,58 @@ extern "C" int b200kv_gather(b200kv_ctx* ctx, const int64_t* slot_mapping, int64
 extern "C" int b200kv_scatter(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
                               const void* dev_chunks, void* stream) {
   return gather_scatter(ctx, slot_mapping, n_tokens, const_cast<void*>(dev_chunks), stream, false);
+}
+
+extern "C" int b200kv_gather_chunks(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                                    const uint64_t* chunk_ptrs, void* stream) {
+  return gather_scatter(ctx, slot_mapping, n_tokens, nullptr, stream, true, chunk_ptrs);
+}
+
+extern "C" int b200kv_scatter_chunks(b200kv_ctx* ctx, const int64_t* slot_mapping, int64_t n_tokens,
+                                     const uint64_t* chunk_ptrs, void* stream) {
+  return gather_scatter(ctx, slot_mapping, n_tokens, nullptr, stream, false, chunk_ptrs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device chunk tier: a buffer of chunk-format slots in HBM, exported to peer replicas over CUDA IPC.
+// The index (which key sits in which slot, LRU, pins) is a b200kv_pool in shm owned by the host side.
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200kv_tier_create(b200kv_ctx* ctx, uint32_t n_slots, uint64_t* base_out) {
+  if (!ctx || !n_slots || !base_out) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->tier_base) return B200KV_EEXIST;
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, static_cast<size_t>(n_slots) * ctx->g.chunk_bytes));
+  ctx->tier_base = p;
+  ctx->tier_slots = n_slots;
+  *base_out = reinterpret_cast<uint64_t>(p);
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_tier_export(b200kv_ctx* ctx, b200kv_ipc_desc* desc_out) {
+  if (!ctx || !desc_out || !ctx->tier_base) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::memset(desc_out, 0, sizeof(*desc_out));
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, ctx->tier_base));
+  std::memcpy(desc_out->handle, &h, 64);
+  desc_out->offset = 0;
+  desc_out->alloc_bytes = static_cast<uint64_t>(ctx->tier_slots) * ctx->g.chunk_bytes;
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_tier_import(b200kv_ctx* ctx, const b200kv_ipc_desc* desc, uint64_t* mapped_base_out) {
+  if (!ctx || !desc || !mapped_base_out) return B200KV_EINVAL;
+  DeviceGuard dg(ctx->cfg.device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, desc->handle, 64);
+  void* base = nullptr;
+  CU_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->tier_imports.push_back(base);
+  *mapped_base_out = reinterpret_cast<uint64_t>(base) + desc->offset;
+  return B200KV_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -925,7 +1026,7 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       // dense op-relative token index: chunk i of this batch starts at i*C
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &runs,
-                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &partial);
+                          ctx->cfg.format != B200KV_FMT_RAW ? nullptr : &partial);
       if (rc) return rc;
       sidx[i] = ctx->store_next;
       ctx->store_next = (ctx->store_next + 1) % static_cast<uint32_t>(n_stage);
@@ -950,6 +1051,8 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
     if (ctx->cfg.format == B200KV_FMT_FP8) {
       // a partial chunk is always the last of the op, hence the last of its batch
       rc = launch_fp8_store(ctx, tv.slot->dev, tv, static_cast<uint32_t>(nb), batch_tokens, ctx->s_gather);
+    } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+      rc = launch_q4(ctx, true, tv.slot->dev, tv, 0, runs.size(), ctx->s_gather);
     } else {
       rc = launch_copy_runs<kStore>(ctx, tv.slot->dev, tv, 0, n_full, n_part, ctx->s_gather);
     }
@@ -1053,7 +1156,7 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       std::vector<Run> cf, cp;
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf,
-                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &cp);
+                          ctx->cfg.format != B200KV_FMT_RAW ? nullptr : &cp);
       if (rc) return rc;
       n_full_of[i] = static_cast<uint32_t>(cf.size());
       runs.insert(runs.end(), cf.begin(), cf.end());
@@ -1092,6 +1195,8 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       if (rc) return rc;
       if (ctx->cfg.format == B200KV_FMT_FP8) {
         rc = launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), ctx->s_scatter, pb, np);
+      } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+        rc = launch_q4(ctx, false, tv.slot->dev, tv, 0, runs.size(), ctx->s_scatter, pb, np);
       } else {
         // one launch per chunk keeps the (full, partial) run split of each chunk
         for (size_t i = 0; i < nb && rc == B200KV_OK; ++i)
@@ -1124,7 +1229,7 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       std::vector<Run> cf, cp;  // per chunk: whole tiles first, then HND partial-tile runs
       int rc = build_runs(ctx, slot_mapping, tb, tb + t.n_tok, tb - static_cast<int64_t>(i) * g.C, &cf,
-                          ctx->cfg.format == B200KV_FMT_FP8 ? nullptr : &cp);
+                          ctx->cfg.format != B200KV_FMT_RAW ? nullptr : &cp);
       if (rc) return rc;
       n_full_of[i] = static_cast<uint32_t>(cf.size());
       runs.insert(runs.end(), cf.begin(), cf.end());
@@ -1157,6 +1262,8 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
       const size_t r0 = offs[i], rn = offs[i + 1] - offs[i];
       if (ctx->cfg.format == B200KV_FMT_FP8) {
         rc = launch_fp8_load(ctx, tv.slot->dev, tv, r0, rn, ctx->s_scatter);
+      } else if (ctx->cfg.format == B200KV_FMT_Q4) {
+        rc = launch_q4(ctx, false, tv.slot->dev, tv, r0, rn, ctx->s_scatter);
       } else {
         rc = launch_copy_runs<kLoad>(ctx, tv.slot->dev, tv, r0, n_full_of[i], rn - n_full_of[i], ctx->s_scatter);
       }

@@ -510,6 +510,23 @@ extern "C" int b200kv_pool_lookup_owner(b200kv_pool* pool, const uint64_t* keys,
   return B200KV_OK;
 }
 
+extern "C" int b200kv_pool_contains(b200kv_pool* pool, const uint64_t* keys, const int32_t* chunk_tokens,
+                                    int32_t n_keys, uint32_t lease_ms, uint8_t* present) {
+  if (!pool || n_keys < 0 || (n_keys > 0 && (!keys || !present))) return B200KV_EINVAL;
+  b200kv_pool::Guard g(pool);
+  const uint64_t lease = now_ns() + static_cast<uint64_t>(lease_ms) * 1000000ull;
+  for (int32_t i = 0; i < n_keys; ++i) {
+    const uint32_t s = pool->find(keys[i]);
+    present[i] = 0;
+    if (s == kNone) continue;
+    Slot& e = pool->slots[s];
+    if (e.state != kReady || (chunk_tokens && e.n_tokens != chunk_tokens[i])) continue;
+    if (lease_ms && e.lease_until_ns < lease) e.lease_until_ns = lease;
+    present[i] = 1;
+  }
+  return B200KV_OK;
+}
+
 extern "C" int b200kv_pool_reserve(b200kv_pool* pool, uint64_t key, int32_t n_tokens,
                                    uint32_t fmt, uint32_t owner, uint32_t* slot_out) {
   if (!pool || !slot_out || n_tokens <= 0) return B200KV_EINVAL;

@@ -142,3 +142,26 @@ def test_adapter_arithmetic():
     assert ko.plan_save(700, 900, 512, 256, discard_partial_chunks=False) is None     # below next boundary
     assert ko.plan_save(900, 900, 512, 256, discard_partial_chunks=False) == (512, 900)
     assert ko.plan_save(901, 900, 900, 256, False, is_decode_phase=True) is None
+
+
+def test_q4_groupwise_codec_spec():
+    """The sub-8-bit format is specified in the oracle before any kernel exists: size,
+    tolerance, exactness on representable inputs, idempotence of re-quantisation."""
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal((2, 2, 37, 4, 128)) * np.exp(rng.uniform(-4, 4, (2, 2, 37, 4, 1)))).astype(np.float32)
+    x[0, 0, 0, 0, :32] = 0.0                                    # an all-zero group
+    bits = ko.f32_to_bf16_bits_rn(x)
+    xb = ko.bf16_bits_to_f32(bits)
+    codes, scales = ko.q4_pack_chunk(bits)
+    assert codes.shape == (2, 2, 37, 4, 64) and scales.shape == (2, 2, 37, 4, 4) and scales.dtype == np.uint16
+    assert codes.nbytes + scales.nbytes == bits.nbytes * 576 // 2048           # 4.5 bits per element
+    back = ko.bf16_bits_to_f32(ko.q4_unpack_chunk(codes, scales))
+    assert np.all(np.abs(back - xb) <= ko.q4_tolerance(xb))
+    assert not back[0, 0, 0, 0, :32].any()
+    codes2, scales2 = ko.q4_pack_chunk(ko.q4_unpack_chunk(codes, scales))       # idempotent
+    assert np.array_equal(ko.q4_unpack_chunk(codes2, scales2), ko.q4_unpack_chunk(codes, scales))
+    # values that are exact multiples of a bf16-exact step round-trip exactly
+    q = rng.integers(-7, 8, (1, 2, 5, 4, 128)).astype(np.float32)
+    q[..., ::32] = 7.0                                           # pins absmax = 7 * step in every group
+    y = ko.f32_to_bf16_bits_rn(q * np.float32(0.125))
+    assert np.array_equal(ko.q4_unpack_chunk(*ko.q4_pack_chunk(y)), y)

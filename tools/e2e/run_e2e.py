@@ -6,6 +6,7 @@ Modes:
   none      no connector, prefix caching off   -> every turn re-prefills its whole context
   b200kv    this repo's connector, RAW (bit-exact) format
   b200kv8   this repo's connector, FP8 packed format
+  b200kvq4  this repo's connector, Q4 group-wise 4-bit format (experimental)
   b200kv_cw / b200kv8_cw      chunk-wise loads (layer-wise overlap with the forward pass switched off)
   b200kv_async / b200kv_c64  variants: loads detached from the forward step / 64-token chunks
   offload   vLLM's in-tree CPU offload connector (same plugin slot; the runnable same-box stand-in
@@ -39,7 +40,7 @@ def connector_args(mode: str, cpu_gb: float):
         # b200kv | b200kv8 (fp8) | b200kv_async (detached loads) | b200kv_c64 (64-token chunks)
         env.update(LMCACHE_LOCAL_CPU="True", LMCACHE_MAX_LOCAL_CPU_SIZE=str(cpu_gb),
                    LMCACHE_CHUNK_SIZE="64" if "c64" in mode else "256",
-                   B200KV_FORMAT="fp8" if "8" in mode.replace("c64", "") else "raw",
+                   B200KV_FORMAT="q4" if "q4" in mode else ("fp8" if "8" in mode.replace("c64", "") else "raw"),
                    B200KV_ASYNC_LOAD="1" if "async" in mode else "0",
                    B200KV_LAYERWISE="0" if "cw" in mode else "1")
         cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}

@@ -13,6 +13,8 @@ Modes:
   private    connector, one pool per replica -> a turn hits only if it lands where its history was stored
   shared     connector, one pool per box     -> any replica retrieves what any other stored (one PCIe hop)
   shared8    shared, FP8 packed format
+  tier       connector, one pool per replica + the device chunk tier (B200KV_DEVICE_TIER_GB=8): a turn that
+             lands on the other replica is scattered straight from the owner's HBM over NVLink
   remote     connector, one pool per replica + the cache-server tier (`python -m b200kv.server`,
              LMCACHE_REMOTE_URL=lm://127.0.0.1:8095): a turn that lands on the other replica is fetched
              from the server into the local pinned pool, then loaded
@@ -71,6 +73,8 @@ def replica_env(mode: str, gpu: int, cpu_gb: float, pool_tag: str) -> tuple[dict
         env["B200KV_POOL_NAME"] = f"/b200kv-box-{pool_tag}"
     if mode.startswith("remote"):
         env["LMCACHE_REMOTE_URL"] = "lm://127.0.0.1:8095"
+    if mode.startswith("tier"):
+        env["B200KV_DEVICE_TIER_GB"] = "8"
     cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}
     return env, ["--kv-transfer-config", json.dumps(cfg)]
 

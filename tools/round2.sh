@@ -11,7 +11,7 @@ mkdir -p "$out"
 stage="${1:-kernels}"
 case "$stage" in
   kernels)
-    python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee "$out/pytest_gpu.txt"
+    python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee "$out/pytest_gpu.txt"   # no -x: collect every failure of the experimental paths in one go
     python tools/microbench.py --out "$out/microbench.json" > "$out/microbench.log" 2>&1
     if grep -q B200KV_FP8_2PASS production-stack_b200/csrc/b200kv_engine.cu; then   # experimental kernel present
       B200KV_FP8_2PASS=1 python tools/microbench.py --out "$out/microbench_2pass.json" > "$out/microbench_2pass.log" 2>&1
@@ -23,7 +23,9 @@ case "$stage" in
     ;;
   multi2)
     [ -f tests/test_gpu_device_tier.py ] && python -m pytest tests/test_gpu_device_tier.py -m gpu -q 2>&1 | tail -3 | tee "$out/pytest_tier.txt"
-    python tools/e2e/run_multi.py --replicas 2 --routing roundrobin --modes none,private,shared --log-dir "$out/multi2_rr" 2>&1 | cut -c1-600
+    modes=none,private,shared
+    grep -q '"tier"' tools/e2e/run_multi.py 2>/dev/null || grep -q 'startswith("tier")' tools/e2e/run_multi.py && modes=none,private,shared,tier
+    python tools/e2e/run_multi.py --replicas 2 --routing roundrobin --modes $modes --log-dir "$out/multi2_rr" 2>&1 | cut -c1-600
     ;;
   routing2)
     python tools/e2e/run_multi.py --replicas 2 --routing roundrobin --modes remote --log-dir "$out/multi2_remote" 2>&1 | cut -c1-600
