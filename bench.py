@@ -94,6 +94,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def slot_map(blocks: np.ndarray, n_tok: int) -> np.ndarray:
+    """slot[i] = block_ids[i // 16] * 16 + i % 16 (vllm_v1_adapter.py:368-375) — input tables only."""
+    i = np.arange(n_tok, dtype=np.int64)
+    return np.asarray(blocks, dtype=np.int64)[i // BS] * BS + i % BS
+
+
+def numa_nodes_of(addr: int) -> dict | None:
+    """Pages per NUMA node of the mapping that contains `addr`, from /proc/self/numa_maps."""
+    try:
+        best = None
+        for ln in open("/proc/self/numa_maps"):
+            f = ln.split()
+            a = int(f[0], 16)
+            if a <= addr and (best is None or a > best[0]):
+                best = (a, f)
+        if best is None:
+            return None
+        out = {}
+        for tok in best[1][1:]:
+            if tok[0] == "N" and "=" in tok and tok[1:].split("=")[0].isdigit():
+                out[tok.split("=")[0]] = int(tok.split("=")[1])
+        return out or None
+    except Exception:
+        return None
+
+
 def session_tokens(rank: int, step: int, s: int) -> np.ndarray:
     """Deterministic synthetic token ids, unique per (rank, step, session) so keys are fresh."""
     base = np.arange(CTX, dtype=np.int64)
@@ -103,20 +129,31 @@ def session_tokens(rank: int, step: int, s: int) -> np.ndarray:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024, target_s: float = 0.0):
+def cpu_oracle_run(steps: int, warmup: int, sessions: int = SESSIONS, nb: int = NB, target_s: float = 0.0,
+                   min_step_s: float = 0.0):
     """store+retrieve of `sessions` x 2K-ctx requests per step with oracle/liboracle.so (gather
-    into a host chunk buffer = the CPU pool, scatter back into other pages).  Returns
-    (GB/s payload, ms/step, threads, sample description).  target_s > 0: the number of steps is
-    chosen so the timed sample is about that many seconds of CPU work (bounded to [steps, 4000])."""
-    from oracle import kv_oracle as ko
+    into a host chunk buffer = the CPU pool, scatter back into other pages) on the SAME configuration
+    the GPU arm advertises: 16 sessions x 2048 tokens over an 8192-block (16 GiB) paged cache in host
+    RAM.  Returns (GB/s payload, ms/step, threads, sample description).  target_s > 0: the number of
+    steps is chosen so the timed sample is about that many seconds of CPU work.  min_step_s > 0: a
+    step repeats the wave until it lasts that long (reference arm: K steps must add up to seconds,
+    not milliseconds).  BENCH_REF_BLOCKS / BENCH_REF_SESSIONS shrink the case for CPU-only CI."""
     from tests import oracle_c
-    rng = np.random.default_rng(0)
-    layers = [rng.integers(0, 2 ** 16, (2, nb, BS, H, D), dtype=np.uint16) for _ in range(L)]
+    sessions = int(os.environ.get("BENCH_REF_SESSIONS", sessions))
+    nb = int(os.environ.get("BENCH_REF_BLOCKS", nb))
+    nblk = CTX // BS
+    nb = max(nb, sessions * nblk)
+    pat = np.random.default_rng(0).integers(0, 2 ** 16, (BS, H, D), dtype=np.uint16)      # one 32 KiB tile
+    layers = []
+    for l in range(L):   # every page touched and distinct per (layer, plane, block); content is irrelevant to timing
+        a = np.empty((2, nb, BS, H, D), dtype=np.uint16)
+        a[:] = pat
+        a[:, :, 0, 0, 0] = np.arange(2 * nb, dtype=np.uint16).reshape(2, nb) + l
+        layers.append(a)
     perm = np.random.default_rng(1234).permutation(nb)
     dperm = np.random.default_rng(4321).permutation(nb)
-    nblk = CTX // BS
-    maps = [(ko.slot_mapping_from_blocks(perm[s * nblk:(s + 1) * nblk], BS, CTX),
-             ko.slot_mapping_from_blocks(dperm[s * nblk:(s + 1) * nblk], BS, CTX)) for s in range(sessions)]
+    maps = [(slot_map(perm[s * nblk:(s + 1) * nblk], CTX), slot_map(dperm[s * nblk:(s + 1) * nblk], CTX))
+            for s in range(sessions)]
     threads = oracle_c.lib().oracle_num_threads()
     keys_out = np.zeros(CTX // C, dtype=np.uint64)
     lib = oracle_c.lib()
@@ -124,7 +161,7 @@ def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024, t
     cb = 2 * L * C * H * D * 2
     pool = np.zeros(sessions * (CTX // C) * cb, dtype=np.uint8)   # the "CPU pool": reused every step
 
-    def one_step(step):
+    def one_wave(step):
         for s, (sm, dm) in enumerate(maps):
             toks = session_tokens(0, step, s)
             lib.oracle_chunk_keys(toks.ctypes.data, CTX, C, 0, 1, keys_out.ctypes.data)
@@ -133,18 +170,21 @@ def cpu_oracle_run(steps: int, warmup: int, sessions: int = 2, nb: int = 1024, t
             lib.oracle_scatter_raw(planes, 2 * L, stride, BS, H * D * 2, dm.ctypes.data, CTX, C, slot.ctypes.data, cb)
 
     for w in range(warmup):
-        one_step(w)
-    if target_s > 0:
-        t0 = time.perf_counter()
-        one_step(warmup)
-        steps = int(min(4000, max(steps, target_s / max(time.perf_counter() - t0, 1e-4))))
+        one_wave(w)
     t0 = time.perf_counter()
-    for k in range(steps):
-        one_step(warmup + k)
+    one_wave(warmup)
+    wave_s = max(time.perf_counter() - t0, 1e-4)
+    reps = max(1, int(np.ceil(min_step_s / wave_s))) if min_step_s > 0 else 1
+    if target_s > 0:
+        steps = int(min(4000, max(steps, target_s / (wave_s * reps))))
+    t0 = time.perf_counter()
+    for k in range(steps * reps):
+        one_wave(warmup + 1 + k)
     dt = time.perf_counter() - t0
-    payload = 2 * sessions * CTX * TOKEN_BYTES_ALL * steps
-    sample = (f"{steps} steps x {sessions} sessions x {CTX} tokens (of {SESSIONS} per GPU step), {dt:.1f} s of CPU work, "
-              f"paged cache {nb} blocks in host RAM, RAW bf16")
+    payload = 2 * sessions * CTX * TOKEN_BYTES_ALL * steps * reps
+    sample = (f"{steps} steps x {reps} wave(s) x {sessions} sessions x {CTX} tokens, {dt:.1f} s of CPU work, "
+              f"paged cache {nb} blocks ({nb * 2 * L * BS * H * D * 2 / 2**30:.0f} GiB) in host RAM, RAW bf16, "
+              f"{threads} threads")
     return payload / dt / 1e9, dt / steps * 1e3, threads, sample
 
 
@@ -152,7 +192,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    gbps, ms, threads, sample = cpu_oracle_run(args.steps, max(args.warmup, 1))
+    # every step lasts >= 1.5 s of CPU work (the wave repeated), so K steps are seconds, not milliseconds
+    gbps, ms, threads, sample = cpu_oracle_run(args.steps, max(args.warmup, 1), min_step_s=1.5)
     line = {
         "impl": "reference", "metric": "kv_offload_GBps", "value": gbps, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -184,8 +225,7 @@ def run_ours(args):
 
     import __graft_entry__ as ge
     ge.build(quiet=True)
-    from b200kv import FMT_FP8, FMT_RAW, KVEngine, KVGeometry, KVPool
-    from oracle import kv_oracle as ko  # slot-mapping helper + cpu_baseline leg only
+    from b200kv import FMT_FP8, FMT_Q4, FMT_RAW, KVEngine, KVGeometry, KVPool
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,18 +234,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: the b200kv engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    # keep this rank's host pool on the GPU's own NUMA node (first-touch happens when the pool is
-    # pinned): on a two-socket HGX box half of the GPUs would otherwise cross UPI on every DMA
-    numa = None
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local)
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        numa = sorted(os.sched_getaffinity(0))
-        numa = f"{numa[0]}-{numa[-1]} ({len(numa)} cpus)"
-    except Exception as e:  # affinity is an optimisation, never a requirement
-        numa = f"unavailable: {e!r}"[:80]
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -221,6 +249,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_objects(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
     geom = KVGeometry(L, H, D, NB, BS, C, 2, 0, FMT_RAW)
     g = torch.Generator(device=dev).manual_seed(rank)
     caches = [torch.randn((2, NB, BS, H, D), generator=g, device=dev, dtype=torch.float32).bfloat16()
@@ -232,12 +267,16 @@ def run_ours(args):
     # held back by store traffic (production default is 1 GiB, B200KV_STAGING_MB)
     eng = KVEngine(geom, pool, local, staging_bytes=2 * n_chunks_step * geom.chunk_bytes, owner=rank)
     eng.register_kv_caches(caches)
+    # where the engine put this rank's pinned pool (it binds the pages to the GPU's own NUMA node when it
+    # pins them, csrc/b200kv_engine.cu place_pool_pages) and where the kernel says they are
+    placement = {"rank": rank, "policy": eng.numa_placement(),
+                 "pages_per_node": numa_nodes_of(pool.slot_view(0).ctypes.data)}
 
     perm = torch.randperm(NB, generator=torch.Generator().manual_seed(1234)).numpy()
     dperm = torch.randperm(NB, generator=torch.Generator().manual_seed(4321)).numpy()
     nblk = CTX // BS
-    src_maps = [ko.slot_mapping_from_blocks(perm[s * nblk:(s + 1) * nblk], BS, CTX) for s in range(SESSIONS)]
-    dst_maps = [ko.slot_mapping_from_blocks(dperm[s * nblk:(s + 1) * nblk], BS, CTX) for s in range(SESSIONS)]
+    src_maps = [slot_map(perm[s * nblk:(s + 1) * nblk], CTX) for s in range(SESSIONS)]
+    dst_maps = [slot_map(dperm[s * nblk:(s + 1) * nblk], CTX) for s in range(SESSIONS)]
     all_src = np.concatenate(src_maps)
     all_dst = np.concatenate(dst_maps)
     stream = torch.cuda.current_stream()
@@ -269,7 +308,8 @@ def run_ours(args):
     ev1.record(stream)
     torch.cuda.synchronize()
     barrier()
-    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    my_e2e_ms = ev0.elapsed_time(ev1) / args.steps
+    e2e_ms = max_over_ranks(my_e2e_ms)
     st1 = eng.stats()
     e2e_payload = 2 * SESSIONS * CTX * TOKEN_BYTES_ALL
     e2e_gbps = world * e2e_payload / (e2e_ms * 1e-3) / 1e9
@@ -304,6 +344,47 @@ def run_ours(args):
     g_ms = float(np.mean([a for a, _ in gather_ms]))
     s_ms = float(np.mean([b for _, b in gather_ms]))
 
+    # ---- decode-jitter leg (extra): a fixed compute kernel on the compute stream, alone and while a
+    # 4 GiB store wave drains through the engine's low-priority streams ----------
+    jitter = None
+    if rank == 0:
+        try:
+            xa = torch.randn((4096, 4096), device=dev, dtype=torch.bfloat16)
+            xb = torch.randn((4096, 4096), device=dev, dtype=torch.bfloat16)
+            big = torch.empty(1 << 28, device=dev, dtype=torch.bfloat16)     # 512 MiB: a decode step is HBM-bound
+
+            def decode_like():           # weight-streaming (HBM) + a small GEMM, ~0.3 ms like one decode layer group
+                big.mul_(1.0)
+                torch.mm(xa, xb)
+
+            def time_steps(n, with_store):
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+                tick = []
+                if with_store:
+                    toks = [session_tokens(rank, 5000 + with_store, s_) for s_ in range(SESSIONS)]
+                    tick = [eng.store(toks[s_], None, src_maps[s_], stream=stream) for s_ in range(SESSIONS)]
+                for e0, e1 in evs:
+                    e0.record(stream)
+                    decode_like()
+                    e1.record(stream)
+                torch.cuda.synchronize()
+                for t_ in tick:
+                    eng.wait(t_)
+                return np.array([e0.elapsed_time(e1) for e0, e1 in evs])
+
+            time_steps(20, 0)
+            quiet = time_steps(200, 0)
+            busy = np.concatenate([time_steps(200, k + 1) for k in range(3)])
+            jitter = {"kernel": "512 MiB bf16 elementwise + 4096^3 bf16 GEMM per step, 200 steps",
+                      "alone_ms_p50": float(np.median(quiet)), "alone_ms_p99": float(np.percentile(quiet, 99)),
+                      "during_store_wave_ms_p50": float(np.median(busy)), "during_store_wave_ms_p99": float(np.percentile(busy, 99)),
+                      "slowdown_p50": float(np.median(busy) / np.median(quiet)),
+                      "note": "store wave = 16 x 2048-token requests (4 GiB gathered + D2H) issued right before the steps; "
+                              "gather kernels run on a lowest-priority stream, D2H on the copy engine"}
+            del xa, xb, big
+        except Exception as e:
+            jitter = {"error": repr(e)}
+
     # ---- peer-pull leg (N>1 only; extra): every rank pulls one wave out of its neighbour's HBM ----
     peer = None
     if world > 1:
@@ -312,112 +393,154 @@ def run_ours(args):
             descs = exchange_kv_descriptors(eng)
             connect_all_peers(eng, descs, rank, device_of_rank=lambda r: r)
             nb_rank = (rank + 1) % world
+            # destination pages disjoint from every rank's source pages, so what a neighbour reads is stable
+            n_wave_blocks = SESSIONS * nblk
+            pull_dst = slot_map(perm[n_wave_blocks:2 * n_wave_blocks], SESSIONS * CTX)
+            src_blocks = torch.as_tensor(perm[:n_wave_blocks].copy(), device=dev)
+            dst_blocks = torch.as_tensor(perm[n_wave_blocks:2 * n_wave_blocks].copy(), device=dev)
+            wts = (torch.arange(BS * H * D, device=dev, dtype=torch.int64) % 65521 + 1)
+
+            def block_sums(blocks):       # position-weighted checksum per (layer, K|V, block): [L, 2, n] int64
+                out = torch.empty((L, 2, len(blocks)), dtype=torch.int64, device=dev)
+                for l in range(L):
+                    x = caches[l].view(torch.int16)[:, blocks].reshape(2, len(blocks), -1).to(torch.int64)
+                    out[l] = (x * wts).sum(-1)
+                return out
+
+            mine = block_sums(src_blocks)
+            all_sums = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(all_sums, mine)
             for w in range(max(args.warmup, 1)):
-                eng.wait(eng.peer_pull(nb_rank, all_src, all_dst, stream=stream))
+                eng.wait(eng.peer_pull(nb_rank, all_src, pull_dst, stream=stream))
             barrier()
             ev0.record(stream)
             for k in range(args.steps):
-                eng.peer_pull(nb_rank, all_src, all_dst, stream=stream)
+                eng.peer_pull(nb_rank, all_src, pull_dst, stream=stream)
             ev1.record(stream)   # the compute stream waits for every pull
             torch.cuda.synchronize()
             barrier()
             pull_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
             kern_ms = eng.last_kernel_ms(2)
+            # every pulled page must equal the neighbour's source page (all layers, K and V, all blocks of the wave)
+            bad = int((block_sums(dst_blocks) != all_sums[nb_rank]).sum().item())
+            bad_total = sum(gather_objects(bad))
             per_gpu = SESSIONS * CTX * TOKEN_BYTES_ALL / (pull_ms * 1e-3) / 1e9
             peer = {"per_gpu_GBps": per_gpu, "aggregate_GBps": per_gpu * world, "ms_per_wave": pull_ms,
                     "kernel_ms": kern_ms, "kernel_GBps": SESSIONS * CTX * TOKEN_BYTES_ALL / (kern_ms * 1e-3) / 1e9,
                     "nvlink_peak_GBps": 770.0, "peak_kind": "B200_PROFILING.md measured peer copy per direction",
                     "frac_of_peak": SESSIONS * CTX * TOKEN_BYTES_ALL / (kern_ms * 1e-3) / 1e9 / 770.0,
-                    "pattern": "rank r reads rank (r+1)%N: in-kernel P2P loads, no staging, no NCCL"}
+                    "pattern": "rank r reads rank (r+1)%N: in-kernel P2P loads, no staging, no NCCL",
+                    "verified": bad_total == 0, "mismatching_tiles": bad_total,
+                    "checked_tiles_per_rank": int(mine.numel()),
+                    "check": "position-weighted int64 checksum of every pulled (layer, K|V, block) tile vs the "
+                             "checksum the owner computed of its source tile before the pulls"}
+            if bad_total:
+                raise SystemExit(f"peer pull moved wrong bytes: {bad_total} tiles differ from the owner's")
+        except SystemExit:
+            raise
         except Exception as e:  # never lose the headline line to the extra leg
             peer = {"error": repr(e)}
 
-    # ---- fp8 leg (extra, not the headline): same wave in FMT_FP8, device-resident + e2e --------
-    fp8 = None
-    if not args.no_fp8:
-        eng.close()
-        pool.close()
-        g8 = KVGeometry(L, H, D, NB, BS, C, 2, 0, FMT_FP8)
-        pool8 = KVPool(None, (n_chunks_step + n_chunks_step // 2) * g8.chunk_bytes, g8.chunk_bytes, 1)
-        e8 = KVEngine(g8, pool8, local, staging_bytes=2 * n_chunks_step * g8.chunk_bytes, owner=rank)
-        e8.register_kv_caches(caches)
-        b8 = torch.empty(n_chunks_step * g8.chunk_bytes, dtype=torch.uint8, device=dev)
+    eng.close()
+    pool.close()
 
-        def fp8_e2e(step):
-            toks = [session_tokens(rank, 1000 + step, s) for s in range(SESSIONS)]
-            tickets = [e8.store(toks[s], None, src_maps[s], stream=stream) for s in range(SESSIONS)]
-            for s in range(SESSIONS):
-                e8.wait(tickets[s])
-                e8.retrieve(toks[s], None, dst_maps[s], stream=stream)
+    # ---- compressed-format legs (extra, not the headline): the same wave in FP8 and Q4 ------------
+    def format_leg(fmt, salt):
+        gq = KVGeometry(L, H, D, NB, BS, C, 2, 0, fmt)
+        poolq = KVPool(None, (n_chunks_step + n_chunks_step // 2) * gq.chunk_bytes, gq.chunk_bytes, 1)
+        eq = KVEngine(gq, poolq, local, staging_bytes=2 * n_chunks_step * gq.chunk_bytes, owner=rank)
+        eq.register_kv_caches(caches)
+        bq = torch.empty(n_chunks_step * gq.chunk_bytes, dtype=torch.uint8, device=dev)
+
+        def q_e2e(step):
+            toks = [session_tokens(rank, salt + step, s_) for s_ in range(SESSIONS)]
+            tickets = [eq.store(toks[s_], None, src_maps[s_], stream=stream) for s_ in range(SESSIONS)]
+            for s_ in range(SESSIONS):
+                eq.wait(tickets[s_])
+                eq.retrieve(toks[s_], None, dst_maps[s_], stream=stream)
 
         for w in range(max(args.warmup, 1)):
-            fp8_e2e(w)
-            e8.gather(all_src, b8.data_ptr(), stream)
-            e8.scatter(all_dst, b8.data_ptr(), stream)
-        torch.cuda.synchronize()
+            q_e2e(w)
+            eq.gather(all_src, bq.data_ptr(), stream)
+            eq.scatter(all_dst, bq.data_ptr(), stream)
+        barrier()
         ev0.record(stream)
         for k in range(args.steps):
-            fp8_e2e(args.warmup + k)
-        e8.wait_all()
+            q_e2e(args.warmup + k)
+        eq.wait_all()
         ev1.record(stream)
         torch.cuda.synchronize()
-        f_e2e_ms = ev0.elapsed_time(ev1) / args.steps
+        barrier()
+        q_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
         km = []
         for k in range(args.steps):
-            e8.gather(all_src, b8.data_ptr(), stream)
-            e8.scatter(all_dst, b8.data_ptr(), stream)
-            km.append((e8.last_kernel_ms(0), e8.last_kernel_ms(1)))
+            eq.gather(all_src, bq.data_ptr(), stream)
+            eq.scatter(all_dst, bq.data_ptr(), stream)
+            km.append((eq.last_kernel_ms(0), eq.last_kernel_ms(1)))
         torch.cuda.synchronize()
-        fp8 = {"e2e_tokens_per_s": SESSIONS * CTX * 2 / (f_e2e_ms * 1e-3),
-               "e2e_equiv_bf16_GBps": e2e_payload / (f_e2e_ms * 1e-3) / 1e9,
-               "pack_kernel_ms": float(np.mean([a for a, _ in km])),
-               "unpack_kernel_ms": float(np.mean([b for _, b in km])),
-               "pack_kernel_algo_GBps": SESSIONS * CTX * (TOKEN_BYTES_ALL * 3 // 2 + 8) / (np.mean([a for a, _ in km]) * 1e-3) / 1e9}
-        e8.close()
-        pool8.close()
-    else:
-        eng.close()
-        pool.close()
+        pack, unpack = float(np.mean([a_ for a_, _ in km])), float(np.mean([b_ for _, b_ in km]))
+        algo = SESSIONS * CTX * (TOKEN_BYTES_ALL + gq.payload_bytes_per_token)      # HBM read bf16 + write packed
+        res = {"e2e_tokens_per_s": world * SESSIONS * CTX * 2 / (q_ms * 1e-3),
+               "e2e_equiv_bf16_GBps": world * e2e_payload / (q_ms * 1e-3) / 1e9, "e2e_ms_per_step": q_ms,
+               "host_link_bytes_per_token": gq.payload_bytes_per_token,
+               "pack_kernel_ms": pack, "unpack_kernel_ms": unpack,
+               "pack_kernel_algo_GBps": algo / (pack * 1e-3) / 1e9, "unpack_kernel_algo_GBps": algo / (unpack * 1e-3) / 1e9}
+        eq.close()
+        poolq.close()
+        del bq
+        return res
 
-    # ---- host-link ceiling for the e2e number (measured live, rank 0 only, N=1 only) -------------
-    link = None
-    if rank == 0 and world == 1:
+    fp8 = q4 = None
+    if not args.no_fp8:
+        fp8 = format_leg(FMT_FP8, 1000)
         try:
-            nbytes = 1 << 30
-            h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-            h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-            d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-
-            def timed(fn, reps=3):
-                fn()
-                torch.cuda.synchronize()
-                ev0.record(stream)
-                for _ in range(reps):
-                    fn()
-                ev1.record(stream)
-                torch.cuda.synchronize()
-                return ev0.elapsed_time(ev1) / reps
-
-            def both():
-                s1.wait_stream(stream)
-                s2.wait_stream(stream)
-                with torch.cuda.stream(s1):
-                    d_a.copy_(h_a, non_blocking=True)
-                with torch.cuda.stream(s2):
-                    h_b.copy_(d_b, non_blocking=True)
-                stream.wait_stream(s1)
-                stream.wait_stream(s2)
-
-            link = {"h2d_GBps": nbytes / timed(lambda: d_a.copy_(h_a, non_blocking=True)) / 1e6,
-                    "d2h_GBps": nbytes / timed(lambda: h_b.copy_(d_b, non_blocking=True)) / 1e6,
-                    "duplex_total_GBps": 2 * nbytes / timed(both) / 1e6,
-                    "how": "cudaMemcpyAsync of 1 GiB pinned (cudaHostAlloc) buffers, CUDA events, this run"}
-            del h_a, h_b, d_a, d_b
+            q4 = format_leg(FMT_Q4, 2000)
         except Exception as e:
-            link = {"error": repr(e)}
+            q4 = {"error": repr(e)}
 
+    # ---- host-link ceiling for the e2e number: measured live at EVERY N, all ranks copying at once ---
+    link = None
+    try:
+        nbytes = 1 << 30
+        h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def timed(fn, reps=4):
+            fn()
+            barrier()
+            ev0.record(stream)
+            for _ in range(reps):
+                fn()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            mine_ms = ev0.elapsed_time(ev1) / reps
+            barrier()
+            return max_over_ranks(mine_ms)
+
+        def both():
+            s1.wait_stream(stream)
+            s2.wait_stream(stream)
+            with torch.cuda.stream(s1):
+                d_a.copy_(h_a, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_b.copy_(d_b, non_blocking=True)
+            stream.wait_stream(s1)
+            stream.wait_stream(s2)
+
+        link = {"h2d_GBps": world * nbytes / timed(lambda: d_a.copy_(h_a, non_blocking=True)) / 1e6,
+                "d2h_GBps": world * nbytes / timed(lambda: h_b.copy_(d_b, non_blocking=True)) / 1e6,
+                "duplex_total_GBps": world * 2 * nbytes / timed(both) / 1e6,
+                "how": f"cudaMemcpyAsync of 1 GiB pinned (cudaHostAlloc) buffers on all {world} GPU(s) at the same time, "
+                       "CUDA events, max over ranks, this run (aggregate over the GPUs)"}
+        del h_a, h_b, d_a, d_b
+    except Exception as e:
+        link = {"error": repr(e)}
+
+    per_rank = gather_objects({**placement, "e2e_ms_per_step": my_e2e_ms,
+                               "e2e_GBps": e2e_payload / (my_e2e_ms * 1e-3) / 1e9})
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -426,17 +549,16 @@ def run_ours(args):
     pk, pk_kind = peaks()
     launch_tokens = SESSIONS * CTX
     achieved = launch_tokens * ALGO_BYTES_PER_TOKEN / (g_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_gather.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "static: " + str(tj.get("source", "ncu --set full capture under profiles/")) + \
+                          " (not re-measured in this run; a bench run is never profiled)"
         except Exception:
             traffic = None
-    try:  # the CPU baseline may use every host core again
-        os.sched_setaffinity(0, range(os.cpu_count()))
-    except Exception:
-        pass
     cpu_gbps, cpu_ms, cpu_threads, cpu_sample = cpu_oracle_run(3, 1, target_s=10.0)
     line = {
         "metric": "kv_offload_GBps", "value": value_gbps, "unit": "GB/s", "n_gpus": world,
@@ -453,16 +575,20 @@ def run_ours(args):
                      "peak_kind": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
                      "launch_ms": g_ms, "scatter_launch_ms": s_ms,
                      "scatter_achieved": launch_tokens * ALGO_BYTES_PER_TOKEN / (s_ms * 1e-3) / 1e9,
-                     "algo_bytes_per_launch": launch_tokens * ALGO_BYTES_PER_TOKEN, "traffic": traffic},
+                     "algo_bytes_per_launch": launch_tokens * ALGO_BYTES_PER_TOKEN, "traffic": traffic,
+                     "traffic_source": traffic_src},
         "roofline_e2e": None if not link or "error" in link else {
-            "bound": "pcie", "achieved": e2e_gbps, "peak": link["duplex_total_GBps"], "unit": "GB/s",
-            "frac": e2e_gbps / link["duplex_total_GBps"],
-            "note": "store D2H and retrieve H2D overlap (full duplex); peak = measured duplex pinned copy", **link},
+            "bound": "host link (PCIe + host memory system)", "achieved": e2e_gbps, "peak": link["duplex_total_GBps"],
+            "unit": "GB/s", "frac": e2e_gbps / link["duplex_total_GBps"],
+            "note": f"store D2H and retrieve H2D overlap (full duplex); peak = duplex pinned copy measured with all "
+                    f"{world} GPU(s) copying at once, i.e. the ceiling this box gives {world} replica(s)", **link},
+        "per_rank": per_rank,
         "cpu_baseline": {"value": cpu_gbps, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                          "sample": cpu_sample, "ms_per_step": cpu_ms},
         "clocks": clocks,
-        "cpu_affinity_rank0": numa,
         "fp8": fp8,
+        "q4": q4,
+        "decode_jitter": jitter,
         "peer_pull": peer,
     }
     print(json.dumps(line), flush=True)

@@ -199,8 +199,15 @@ typedef struct b200kv_engine_config {
   int32_t stages;            /* smem ring depth for BULK (0 = default)                       */
   int32_t ctas_per_sm;       /* persistent CTAs per SM (0 = default)                         */
   int32_t kv_layout;         /* B200KV_LAYOUT_*: order inside one (block, K|V) tile            */
-  int32_t reserved;
+  int32_t numa_policy;       /* B200KV_NUMA_*: where the pool's host pages are placed when this
+                              * engine is the first to pin them (0 = the GPU's own node)         */
 } b200kv_engine_config;
+
+/* Host-page placement of the pinned pool (the reference leaves it to first touch: LMCache's
+ * LocalCPUBackend allocates with torch pin_memory, deployment-vllm-multi.yaml:326-333 only sizes it). */
+#define B200KV_NUMA_LOCAL 0      /* prefer the NUMA node the GPU hangs off (per-engine pools)      */
+#define B200KV_NUMA_INTERLEAVE 1 /* interleave over all nodes (one pool shared by a box's replicas) */
+#define B200KV_NUMA_OFF 2        /* leave it to the kernel's first-touch policy                     */
 
 typedef struct b200kv_engine_stats {
   uint64_t n_store_ops, n_load_ops, n_pull_ops;
@@ -213,6 +220,9 @@ typedef struct b200kv_engine_stats {
 /* Engine construction (stands in for _init_lmcache_engine, vllm_v1_adapter.py:433-558).
  * `pool` may be NULL for an engine used only through gather/scatter/peer_pull.             */
 int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool* pool, b200kv_ctx** out);
+/* What the engine did about host-page placement when it pinned the pool (numa_policy above), as text
+ * for logs and bench output, e.g. "mbind preferred node 1".                                  */
+int b200kv_engine_numa_placement(b200kv_ctx* ctx, char* buf, uint64_t n);
 int b200kv_engine_destroy(b200kv_ctx* ctx);
 /* chunk_bytes for this engine's format — slot_bytes a pool must be created with.           */
 int64_t b200kv_engine_chunk_bytes(const b200kv_engine_config* cfg);

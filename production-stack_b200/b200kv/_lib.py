@@ -16,6 +16,7 @@ FMT_RAW, FMT_FP8, FMT_Q4 = 0, 1, 2   # FMT_Q4: experimental (group-wise 4-bit)
 VARIANT_BULK, VARIANT_LDG = 0, 1
 LAYOUT_NHD, LAYOUT_HND = 0, 1
 POOL_CREATE, POOL_ATTACH, POOL_CREATE_OR_ATTACH = 1, 2, 3
+NUMA_LOCAL, NUMA_INTERLEAVE, NUMA_OFF = 0, 1, 2
 
 OK, EINVAL, ENOMEM, ENODEV, ENOENT, EEXIST, ENOSPC, ENOTSUP, EBUSY = 0, -22, -12, -19, -2, -17, -28, -95, -16
 
@@ -42,7 +43,7 @@ class EngineConfig(C.Structure):
                 ("block_stride_bytes", C.c_uint64), ("n_blocks", C.c_uint64),
                 ("staging_bytes", C.c_uint64), ("owner", C.c_uint32), ("variant", C.c_int32),
                 ("stages", C.c_int32), ("ctas_per_sm", C.c_int32), ("kv_layout", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("numa_policy", C.c_int32)]
 
 
 class EngineStats(C.Structure):
@@ -89,6 +90,7 @@ SIGNATURES = {
     "b200kv_pool_check": (C.c_int, [_P]),
     "b200kv_engine_create": (C.c_int, [C.POINTER(EngineConfig), _P, C.POINTER(_P)]),
     "b200kv_engine_destroy": (C.c_int, [_P]),
+    "b200kv_engine_numa_placement": (C.c_int, [_P, C.c_char_p, C.c_uint64]),
     "b200kv_engine_chunk_bytes": (C.c_int64, [C.POINTER(EngineConfig)]),
     "b200kv_register_kv": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "b200kv_store_async": (C.c_int, [_P, _U64P, C.c_int32, _I64P, C.c_int64, _P, _U64P]),

@@ -221,7 +221,11 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._rank = rank
         self._engine = KVEngine(geom, self._pool, device=t0.device.index or 0,
                                 staging_bytes=self.cfg.staging_mb << 20, owner=owner_tag_of(self.cfg.instance_id),
-                                variant=self.cfg.variant, key_seed=self._key_seed(rank))
+                                variant=self.cfg.variant, key_seed=self._key_seed(rank),
+                                # a pool shared by the box's replicas is interleaved over the sockets, a
+                                # per-engine pool lives on the GPU's own node
+                                numa_policy=_lib.NUMA_INTERLEAVE if self.cfg.pool_name else _lib.NUMA_LOCAL)
+        logger.info("b200kv pool pages: %s", self._engine.numa_placement())
         self._engine.register_kv_caches(tensors)
         self._layer_index = {name: i for i, name in enumerate(kv_caches.keys())}
         self._layer_hooks_seen = 0

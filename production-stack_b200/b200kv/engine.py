@@ -89,11 +89,11 @@ class KVGeometry:
         return xxh64(tag, DEFAULT_SEED)
 
     def to_c(self, device: int, staging_bytes: int, owner: int, variant: int, stages: int,
-             ctas_per_sm: int) -> _lib.EngineConfig:
+             ctas_per_sm: int, numa_policy: int = 0) -> _lib.EngineConfig:
         return _lib.EngineConfig(device, self.n_layers, self.n_kv_heads, self.head_dim,
                                  self.elem_bytes, self.block_tokens, self.chunk_tokens, self.fmt,
                                  self.stride, self.n_blocks, staging_bytes, owner, variant, stages,
-                                 ctas_per_sm, self.layout, 0)
+                                 ctas_per_sm, self.layout, numa_policy)
 
     @property
     def chunk_bytes(self) -> int:
@@ -274,12 +274,13 @@ class KVEngine:
 
     def __init__(self, geom: KVGeometry, pool: KVPool | None, device: int = 0,
                  staging_bytes: int = 1 << 30, owner: int = 0, variant: int = VARIANT_BULK,
-                 stages: int = 0, ctas_per_sm: int = 0, key_seed: int | None = None):
+                 stages: int = 0, ctas_per_sm: int = 0, key_seed: int | None = None,
+                 numa_policy: int = _lib.NUMA_LOCAL):
         self.geom = geom
         self.pool = pool
         self.device = device
         self.key_seed = geom.key_seed() if key_seed is None else key_seed
-        cfg = geom.to_c(device, staging_bytes, owner, variant, stages, ctas_per_sm)
+        cfg = geom.to_c(device, staging_bytes, owner, variant, stages, ctas_per_sm, numa_policy)
         h = C.c_void_p()
         check(lib().b200kv_engine_create(C.byref(cfg), pool.handle if pool else None, C.byref(h)),
               "b200kv_engine_create")
@@ -468,6 +469,12 @@ class KVEngine:
         s = _lib.EngineStats()
         check(lib().b200kv_engine_get_stats(self._h, C.byref(s)), "b200kv_engine_get_stats")
         return s.as_dict()
+
+    def numa_placement(self) -> str:
+        """Where the pool's host pages were put when this engine pinned them (text, for logs)."""
+        buf = C.create_string_buffer(160)
+        check(lib().b200kv_engine_numa_placement(self._h, buf, len(buf)), "b200kv_engine_numa_placement")
+        return buf.value.decode()
 
     def last_kernel_ms(self, which: int) -> float:
         ms = C.c_float(0)

@@ -13,6 +13,7 @@
 // never for a PCIe transfer of a store.
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +27,10 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "b200kv.h"
 #include "b200kv_kernels.cuh"
@@ -170,6 +175,7 @@ struct b200kv_ctx {
   Geometry g{};
   b200kv_pool* pool = nullptr;
   bool pool_registered = false;
+  std::string numa_placement = "no pool";   // what place_pool_pages() did when this engine pinned the pool
   void* pool_base = nullptr;
   int sm_count = 148;
   std::mutex mu;
@@ -663,6 +669,108 @@ static int engine_create_impl(const b200kv_engine_config* cfg, b200kv_pool* pool
 
 extern "C" int b200kv_engine_destroy(b200kv_ctx* ctx);
 
+extern "C" int b200kv_engine_numa_placement(b200kv_ctx* ctx, char* buf, uint64_t n) {
+  if (!ctx || !buf || n == 0) return B200KV_EINVAL;
+  std::snprintf(buf, n, "%s", ctx->numa_placement.c_str());
+  return B200KV_OK;
+}
+
+// ---- host-page placement of the pinned pool --------------------------------------------------
+// On a two-socket HGX box every DMA of a GPU whose pool pages sit on the other socket crosses the
+// inter-socket link twice as slowly as the PCIe link it came over.  The pages of the pool segment are
+// physically allocated when the first engine pins them (cudaHostRegister faults them in), so the
+// policy is applied to the mapping right before that: mbind() on the shared mapping (shmem keeps the
+// policy with the object, so later attachers inherit it).  Where mbind is filtered (containers without
+// CAP_SYS_NICE) the fallback for NUMA_LOCAL is to run the pinning call on the node's CPUs.
+static int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+  for (char* p = bus; *p; ++p) *p = static_cast<char>(std::tolower(*p));
+  char path[128];
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = std::fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (std::fscanf(f, "%d", &node) != 1) node = -1;
+  std::fclose(f);
+  return node;
+}
+
+static int online_numa_nodes(unsigned long* mask, int* max_node) {
+  *mask = 0;
+  *max_node = -1;
+  FILE* f = std::fopen("/sys/devices/system/node/online", "r");
+  if (!f) return -1;
+  char buf[128] = {0};
+  if (!std::fgets(buf, sizeof(buf), f)) { std::fclose(f); return -1; }
+  std::fclose(f);
+  for (char* p = buf; *p && *p != '\n';) {       // "0-1" or "0,2-3"
+    char* e = nullptr;
+    long a = std::strtol(p, &e, 10), b = a;
+    if (e == p) break;
+    if (*e == '-') { p = e + 1; b = std::strtol(p, &e, 10); }
+    for (long n = a; n <= b && n < 64; ++n) { *mask |= 1ul << n; *max_node = std::max<int>(*max_node, static_cast<int>(n)); }
+    p = (*e == ',') ? e + 1 : e;
+  }
+  return *max_node >= 0 ? 0 : -1;
+}
+
+struct NumaPinScope {       // restores the thread's CPU affinity if the fallback narrowed it
+  cpu_set_t saved;
+  bool narrowed = false;
+  ~NumaPinScope() { if (narrowed) sched_setaffinity(0, sizeof(saved), &saved); }
+};
+
+// returns a short description for the log / stats ("mbind preferred node 1", "affinity node 0", ...)
+static std::string place_pool_pages(void* base, uint64_t bytes, int device, int policy, NumaPinScope* scope) {
+  const char* e = std::getenv("B200KV_POOL_NUMA");       // local | interleave | off overrides the config
+  if (e) policy = !std::strcmp(e, "interleave") ? B200KV_NUMA_INTERLEAVE : !std::strcmp(e, "off") ? B200KV_NUMA_OFF : B200KV_NUMA_LOCAL;
+  if (policy == B200KV_NUMA_OFF) return "first touch (off)";
+  unsigned long online = 0;
+  int max_node = -1;
+  if (online_numa_nodes(&online, &max_node) != 0 || max_node == 0) return "single NUMA node";
+  constexpr int kPreferred = 1, kInterleave = 3;    // MPOL_* of <linux/mempolicy.h>
+  if (policy == B200KV_NUMA_INTERLEAVE) {
+    const long rc = syscall(SYS_mbind, base, static_cast<unsigned long>(bytes), kInterleave, &online, 65ul, 0u);
+    return rc == 0 ? "mbind interleave over online nodes" : std::string("mbind refused (") + std::strerror(errno) + "): first touch";
+  }
+  const int node = gpu_numa_node(device);
+  if (node < 0 || node > max_node) return "GPU NUMA node unknown: first touch";
+  unsigned long mask = 1ul << node;
+  if (syscall(SYS_mbind, base, static_cast<unsigned long>(bytes), kPreferred, &mask, 65ul, 0u) == 0)
+    return "mbind preferred node " + std::to_string(node);
+  const int mbind_errno = errno;
+  // fallback: fault the pages in from a CPU of that node
+  char path[96];
+  std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = std::fopen(path, "r");
+  cpu_set_t want;
+  CPU_ZERO(&want);
+  if (f) {
+    char buf[512] = {0};
+    if (std::fgets(buf, sizeof(buf), f)) {
+      for (char* p = buf; *p && *p != '\n';) {
+        char* q = nullptr;
+        long a = std::strtol(p, &q, 10), b = a;
+        if (q == p) break;
+        if (*q == '-') { p = q + 1; b = std::strtol(p, &q, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET(static_cast<int>(c), &want);
+        p = (*q == ',') ? q + 1 : q;
+      }
+    }
+    std::fclose(f);
+  }
+  if (CPU_COUNT(&want) > 0 && sched_getaffinity(0, sizeof(scope->saved), &scope->saved) == 0) {
+    cpu_set_t both;
+    CPU_AND(&both, &want, &scope->saved);
+    if (CPU_COUNT(&both) > 0 && sched_setaffinity(0, sizeof(both), &both) == 0) {
+      scope->narrowed = true;
+      return std::string("mbind refused (") + std::strerror(mbind_errno) + "): pinned from the CPUs of node " + std::to_string(node);
+    }
+  }
+  return std::string("mbind refused (") + std::strerror(mbind_errno) + "): first touch";
+}
+
 extern "C" int b200kv_engine_create(const b200kv_engine_config* cfg, b200kv_pool* pool,
                                     b200kv_ctx** out) {
   if (!cfg || !out) return B200KV_EINVAL;
@@ -762,6 +870,9 @@ static int engine_create_impl(const b200kv_engine_config* cfg, b200kv_pool* pool
     if (ps.slot_bytes < g.chunk_bytes) return B200KV_EINVAL;
     // Pin the (possibly shared) pool for this process so D2H/H2D run at full PCIe speed and
     // asynchronously.  Portable: every replica on the box registers the same segment.
+    NumaPinScope numa_scope;
+    ctx->numa_placement = place_pool_pages(base, bytes, cfg->device, cfg->numa_policy, &numa_scope);
+    if (env_int("B200KV_VERBOSE", 0)) std::fprintf(stderr, "b200kv: pool pages: %s\n", ctx->numa_placement.c_str());
     const cudaError_t re = cudaHostRegister(base, bytes, cudaHostRegisterPortable);
     if (re == cudaSuccess) {
       ctx->pool_registered = true;

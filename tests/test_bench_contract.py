@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def run(env_extra=None):
-    env = dict(os.environ, ORACLE_THREADS="4", **(env_extra or {}))
+    env = dict(os.environ, ORACLE_THREADS="4", BENCH_REF_BLOCKS="1024", BENCH_REF_SESSIONS="2", **(env_extra or {}))   # CI-sized paged cache
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
                            "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
 

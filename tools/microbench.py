@@ -23,12 +23,14 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "production-stack_b200"))
 import b200kv  # noqa: E402
-from b200kv import FMT_FP8, FMT_RAW, KVEngine, KVGeometry  # noqa: E402
+from b200kv import FMT_FP8, FMT_Q4, FMT_RAW, KVEngine, KVGeometry  # noqa: E402
 
 L, H, D, BS, C, NB = 32, 8, 128, 16, 256, 8192
 SIZES = (256, 2048, 8192, 32768)
 P_BF16 = L * 2 * H * D * 2                       # 131072 B / token
-ALGO = {FMT_RAW: 2 * P_BF16, FMT_FP8: P_BF16 + P_BF16 // 2 + 8}   # §8(d): HBM read + HBM write per token
+ALGO = {FMT_RAW: 2 * P_BF16, FMT_FP8: P_BF16 + P_BF16 // 2 + 8,      # §8(d): HBM read + HBM write per token
+        FMT_Q4: P_BF16 + P_BF16 * 9 // 32}                          # 4 bits + a bf16 scale per 32 elements
+FMT_NAME = {FMT_RAW: "raw", FMT_FP8: "fp8", FMT_Q4: "q4"}
 
 
 def slots_of(blocks: np.ndarray) -> np.ndarray:
@@ -63,6 +65,7 @@ def main():
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.json"))
+    ap.add_argument("--no-torch-baseline", action="store_true")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -76,7 +79,7 @@ def main():
 
     def add(n_tok, fmt, layout, op, call_ms, kern_ms, impl):
         algo = ALGO[fmt] * n_tok
-        r = {"n_tok": n_tok, "format": "raw" if fmt == FMT_RAW else "fp8", "tile": layout, "op": op, "impl": impl,
+        r = {"n_tok": n_tok, "format": FMT_NAME[fmt], "tile": layout, "op": op, "impl": impl,
              "call_ms": round(call_ms, 4), "kernel_ms": None if kern_ms is None else round(kern_ms, 4),
              "algo_bytes": algo, "call_GBps": round(algo / call_ms / 1e6, 1),
              "kernel_GBps": None if kern_ms is None else round(algo / kern_ms / 1e6, 1)}
@@ -95,7 +98,7 @@ def main():
                       .permute(0, 1, 3, 2, 4) for _ in range(L)]
             stride = 2 * BS * H * D * 2
         lay = b200kv._lib.LAYOUT_NHD if layout == "NHD" else b200kv._lib.LAYOUT_HND
-        for fmt in (FMT_RAW, FMT_FP8):
+        for fmt in (FMT_RAW, FMT_FP8, FMT_Q4):
             geom = KVGeometry(L, H, D, NB, BS, C, 2, stride, fmt, lay)
             eng = KVEngine(geom, None, 0, staging_bytes=0)
             eng.register_kv_caches(caches)
@@ -112,7 +115,7 @@ def main():
                 add(n_tok, fmt, layout, "retrieve(scatter)", c, k, "b200kv")
             eng.close()
             del buf
-        if layout == "NHD":
+        if layout == "NHD" and not args.no_torch_baseline:
             # baseline 2(b): LMCache's gather/scatter restated in PyTorch, same pages, same GPU
             for n_tok in SIZES:
                 nblk = n_tok // BS

@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "production-stack_b200"))
-from b200kv import FMT_FP8, FMT_RAW, KVEngine, KVGeometry  # noqa: E402
+from b200kv import FMT_FP8, FMT_Q4, FMT_RAW, KVEngine, KVGeometry  # noqa: E402
 from oracle import kv_oracle as ko  # noqa: E402  (slot-mapping helper only)
 
 L, H, D, BS, C, NB = 32, 8, 128, 16, 256, 8192
@@ -31,7 +31,8 @@ perm = torch.randperm(NB, generator=torch.Generator().manual_seed(1234)).numpy()
 dperm = torch.randperm(NB, generator=torch.Generator().manual_seed(4321)).numpy()
 sm = ko.slot_mapping_from_blocks(perm[: tokens // BS], BS, tokens)
 dm = ko.slot_mapping_from_blocks(dperm[: tokens // BS], BS, tokens)
-for fmt in (FMT_RAW, FMT_FP8):
+fmts = {"raw": FMT_RAW, "fp8": FMT_FP8, "q4": FMT_Q4}
+for fmt in [fmts[f] for f in os.environ.get("PROF_FORMATS", "raw,fp8").split(",")]:
     geom = KVGeometry(L, H, D, NB, BS, C, 2, 2 * BS * H * D * 2 if hnd else 0, fmt, 1 if hnd else 0)
     eng = KVEngine(geom, None, 0, staging_bytes=0, variant=variant)
     eng.register_kv_caches(caches)
