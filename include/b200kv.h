@@ -137,6 +137,10 @@ typedef struct b200kv_pool_stats {
 int b200kv_pool_open(const b200kv_pool_config* cfg, b200kv_pool** out);
 int b200kv_pool_close(b200kv_pool* pool);
 int b200kv_pool_unlink(const char* shm_name);
+/* Remove the named segments /dev/shm/<prefix>* that no live process has open (every opener holds a shared
+ * flock on the segment for its lifetime) and that are at least min_age_s old: what a SIGKILLed or OOM-killed
+ * engine left behind.  The reference's pool dies with its process (torch pinned memory); a shm pool does not. */
+int b200kv_pool_sweep(const char* prefix, int32_t min_age_s, int32_t* n_removed);
 /* Base address / byte length of the payload area (for cudaHostRegister by the engine).    */
 int b200kv_pool_region(b200kv_pool* pool, void** base, uint64_t* bytes);
 void* b200kv_pool_slot_ptr(b200kv_pool* pool, uint32_t slot);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200kv_pool_open": (C.c_int, [C.POINTER(PoolConfig), C.POINTER(_P)]),
     "b200kv_pool_close": (C.c_int, [_P]),
     "b200kv_pool_unlink": (C.c_int, [C.c_char_p]),
+    "b200kv_pool_sweep": (C.c_int, [C.c_char_p, C.c_int32, _I32P]),
     "b200kv_pool_region": (C.c_int, [_P, C.POINTER(_P), _U64P]),
     "b200kv_pool_slot_ptr": (_P, [_P, C.c_uint32]),
     "b200kv_pool_lookup": (C.c_int, [_P, _U64P, _I32P, C.c_int32, C.c_uint32, _I32P, _I64P]),

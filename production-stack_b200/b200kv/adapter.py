@@ -118,6 +118,70 @@ def make_req_meta(tracker: RequestTracker, block_size: int, chunk: int, load_spe
                    load_spec=load_spec)
 
 
+@dataclass
+class KeyIdentity:
+    """What, besides its token ids, decides the KV of a request.  The reference adapter overwrites the
+    multimodal placeholder tokens with (16 bits of) the item's hash before lookup and before store
+    (adapter :198, :344-350, :1168-1172; lmcache_integration/utils.py:63-89,169-209) and carries
+    `request_configs` (the `lmcache.*` kv_transfer_params, adapter :102-117) into the chunk key; vLLM's own
+    prefix cache also separates requests by `cache_salt` and LoRA adapter.  Here all of it is folded into
+    the token stream the chunk keys are hashed from ("key tokens"): placeholder ranges are overwritten
+    with 128 bits of the item's identifier, and a salted request has every token XORed with a 31-bit salt,
+    so it shares no chunk with an unsalted one or with another salt."""
+    salt: int = 0
+    spans: list = field(default_factory=list)     # (offset, length, int32[4] words of the item's identifier)
+
+    def apply(self, tokens, start: int = 0) -> np.ndarray:
+        """Key tokens of `tokens`, which sit at positions [start, start+len) of the request."""
+        out = np.array(tokens, dtype=np.int32, copy=True)
+        if self.salt:
+            out ^= np.int32(self.salt)
+        n = len(out)
+        for off, length, words in self.spans:
+            lo, hi = max(off, start), min(off + length, start + n)
+            if lo < hi:
+                out[lo - start:hi - start] = words[(np.arange(lo, hi) - off) % len(words)]
+        return out
+
+
+def _hash32(data: bytes, seed: int) -> int:
+    from .engine import xxh64
+    return xxh64(data, seed) & 0x7FFFFFFF
+
+
+def request_identity(req) -> KeyIdentity | None:
+    """KeyIdentity of a vLLM Request / NewRequestData, or None when the token ids alone decide the KV."""
+    spans = []
+    feats = getattr(req, "mm_features", None)
+    if feats:
+        items = [(getattr(f, "identifier", None), getattr(f, "mm_position", None)) for f in feats]
+    elif getattr(req, "mm_hashes", None):
+        items = list(zip(req.mm_hashes, getattr(req, "mm_positions", None) or []))
+    else:
+        items = []
+    for ident, pos in items:
+        if ident is None or pos is None:
+            continue
+        b = str(ident).encode()
+        words = np.array([_hash32(b, j) for j in range(4)], dtype=np.int32)
+        spans.append((int(pos.offset), int(pos.length), words))
+    parts = []
+    salt = getattr(req, "cache_salt", None)
+    if salt:
+        parts.append("salt=" + str(salt))
+    lora = getattr(req, "lora_request", None)
+    if lora is not None:
+        parts.append("lora=" + str(getattr(lora, "lora_name", None) or getattr(lora, "lora_int_id", lora)))
+    sp = getattr(req, "sampling_params", None)
+    ktp = ((getattr(sp, "extra_args", None) or {}).get("kv_transfer_params") or {}) if sp is not None else {}
+    tags = sorted((k, str(v)) for k, v in ktp.items() if isinstance(k, str) and k.startswith("lmcache.tag."))
+    if tags:
+        parts.append("tags=" + repr(tags))
+    if not spans and not parts:
+        return None
+    return KeyIdentity((_hash32("|".join(parts).encode(), 0x6B76) or 1) if parts else 0, spans)
+
+
 def request_skip_save(req) -> bool:
     """Per-request opt-out `kv_transfer_params["lmcache.skip_save"]` (adapter :102-117, :311)."""
     sp = getattr(req, "sampling_params", None)
@@ -152,17 +216,25 @@ class SchedulerState:
         self.load_specs: dict[str, LoadSpec] = {}
         self.trackers: dict[str, RequestTracker] = {}
         self.unfinished: dict[str, object] = {}
+        self.identities: dict[str, KeyIdentity] = {}   # requests whose keys are not a function of the tokens alone
         self.num_lookups = 0
         self.num_hit_tokens = 0
         self.num_requested_tokens = 0
 
     # get_num_new_matched_tokens (adapter :1141-1228); side-effect free apart from the lease
+    def key_tokens(self, req_id: str, tokens, start: int = 0):
+        """The token stream chunk keys are hashed from (KeyIdentity); the tokens themselves for plain text."""
+        ident = self.identities.get(req_id)
+        return tokens if ident is None else ident.apply(tokens, start)
+
     def num_new_matched_tokens(self, req_id: str, prompt_token_ids, num_tokens: int,
-                               num_computed_tokens: int, priority: int = 0) -> int:
+                               num_computed_tokens: int, priority: int = 0, identity: KeyIdentity | None = None) -> int:
+        if identity is not None:
+            self.identities[req_id] = identity
         if self.kv_role == "kv_producer":
             return 0
         self._priority[req_id] = priority
-        hit = int(self.lookup(prompt_token_ids))
+        hit = int(self.lookup(self.key_tokens(req_id, prompt_token_ids)))
         self.num_lookups += 1
         self.num_hit_tokens += hit
         self.num_requested_tokens += len(prompt_token_ids)
@@ -184,7 +256,7 @@ class SchedulerState:
             # the request is not part of this step's SchedulerOutput: emit its load on its own
             self.load_specs.pop(rid)
             n = spec.external_cached_tokens
-            toks = (request.prompt_token_ids or [])[:n]
+            toks = self.key_tokens(rid, (request.prompt_token_ids or [])[:n])
             self._pending_async.append(ReqMeta(rid, np.asarray(toks, dtype=np.int32), first_group(block_ids),
                                                load_spec=spec, async_load=True))
             self._async_saved[rid] = n
@@ -200,13 +272,18 @@ class SchedulerState:
             self.load_specs.pop(rid, None)
             self._async_saved.pop(rid, None)
             self._priority.pop(rid, None)
+            self.identities.pop(rid, None)
         for req in scheduler_output.scheduled_new_reqs:
+            if req.req_id not in self.identities:       # normally known since the lookup; producers never look up
+                ident = request_identity(req)
+                if ident is not None:
+                    self.identities[req.req_id] = ident
             spec = self.load_specs.pop(req.req_id, None)
             n_compute = req.num_computed_tokens + scheduler_output.num_scheduled_tokens[req.req_id]
             saved = spec.external_cached_tokens if spec is not None else self._async_saved.pop(req.req_id, 0)
             prompt = req.prompt_token_ids or []
             prio = self._priority.pop(req.req_id, 0)
-            tr = RequestTracker(req.req_id, len(prompt), list(prompt[:n_compute]),
+            tr = RequestTracker(req.req_id, len(prompt), list(self.key_tokens(req.req_id, prompt[:n_compute])),
                                 first_group(req.block_ids), num_saved_tokens=saved,
                                 skip_save=force_skip or request_skip_save(req)
                                 or (self.priority_limit is not None and prio > self.priority_limit))
@@ -229,6 +306,8 @@ class SchedulerState:
                 new_tokens = list(cached.all_token_ids[rid][cur:cur + n_new])
             else:
                 new_tokens = []
+            if new_tokens and rid in self.identities:
+                new_tokens = list(self.key_tokens(rid, new_tokens, cur))
             resumed = rid in getattr(cached, "resumed_req_ids", ())
             if resumed:
                 # Preempted and scheduled again: vLLM recomputes from `num_computed_tokens` (whatever its prefix
@@ -237,7 +316,7 @@ class SchedulerState:
                 # reference adapter appends the new blocks to the old ones here, adapter :214-245.)
                 n_comp = cached.num_computed_tokens[i] if getattr(cached, "num_computed_tokens", None) else 0
                 ids = req.all_token_ids if req is not None else getattr(cached, "all_token_ids", {}).get(rid, tr.token_ids)
-                tr.token_ids = list(ids[: n_comp + n_new])
+                tr.token_ids = list(self.key_tokens(rid, ids[: n_comp + n_new]))
                 tr.allocated_block_ids = first_group(cached.new_block_ids[i])
                 tr.is_decode_phase = False
             else:

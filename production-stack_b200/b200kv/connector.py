@@ -23,7 +23,7 @@ from vllm.distributed.kv_transfer.kv_connector.v1.base import (KVConnectorBase_V
                                                                KVConnectorRole, SupportsHMA)
 
 from . import _lib
-from .adapter import ReqMeta, SchedulerState, WorkerState
+from .adapter import ReqMeta, SchedulerState, WorkerState, request_identity
 from .config import B200KVConfig
 from .engine import KVEngine, KVGeometry, KVPool, paged_layout_of, xxh64
 from .pd import PDMeta, PDScheduler, PDWorker, first_group, publish_ipc, unpublish_ipc
@@ -88,6 +88,12 @@ def owner_tag_of(instance_id: str) -> int:
     return (xxh64(instance_id.encode(), 0) & 0x7FFFFFFF) or 1
 
 
+# per-engine segments carry vLLM's random engine id: nothing ever re-attaches to one whose engine died, so the
+# scheduler role sweeps the unheld ones of earlier incarnations at start-up (k8s keeps a memory-backed emptyDir
+# across container restarts inside a pod: a crash loop would otherwise fill /dev/shm)
+ENGINE_POOL_PREFIX = "/b200kv-eng-"
+
+
 def pool_name_for(vllm_config, cfg: B200KVConfig, chunk_bytes: int = 0) -> str:
     """One segment per engine unless B200KV_POOL_NAME names a shared one (BASELINE.json
     config 3: "shared pinned-host KV pool" across the replicas of a box).  A shared name is
@@ -97,7 +103,7 @@ def pool_name_for(vllm_config, cfg: B200KVConfig, chunk_bytes: int = 0) -> str:
         base = cfg.pool_name if cfg.pool_name.startswith("/") else "/" + cfg.pool_name
         return f"{base}-{chunk_bytes:x}" if chunk_bytes else base
     eid = vllm_config.kv_transfer_config.engine_id or "engine"
-    return "/b200kv-" + "".join(ch for ch in str(eid) if ch.isalnum() or ch in "-_")[:48]
+    return ENGINE_POOL_PREFIX + "".join(ch for ch in str(eid) if ch.isalnum() or ch in "-_")[:48]
 
 
 class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
@@ -125,6 +131,13 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._model = str(vllm_config.model_config.model)
         self._world = pc.tensor_parallel_size
         self._pool_name = pool_name_for(vllm_config, self.cfg, geom.chunk_bytes)
+        if role == KVConnectorRole.SCHEDULER:
+            try:
+                n_swept = KVPool.sweep(ENGINE_POOL_PREFIX, int(self.cfg.extra.get("sweep_min_age_s", 60)))
+                if n_swept:
+                    logger.warning("b200kv: removed %d pool segment(s) left in /dev/shm by engines that died", n_swept)
+            except Exception as e:     # hygiene only
+                logger.debug("b200kv: segment sweep skipped (%s)", e)
         self._pool = KVPool(self._pool_name, self.cfg.pool_bytes, geom.chunk_bytes, _lib.POOL_CREATE_OR_ATTACH)
         self._engine: KVEngine | None = None
         self._worker: WorkerState | None = None
@@ -138,7 +151,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._sched_counters: tuple = (0, 0, 0)   # worker: last counters received from this engine's scheduler
         if role == KVConnectorRole.SCHEDULER:
             self._pd = PDScheduler(self._engine_id, self._block_size,
-                                   lease_s=float(self.cfg.extra.get("pd_lease_s", 120.0)))
+                                   lease_s=float(self.cfg.extra.get("pd_lease_s", 120.0)), tp_size=self._world)
             seed = self._key_seed(0)
             lease = self.cfg.lookup_lease_ms
             chunk = self._chunk
@@ -250,8 +263,9 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             if self._remote is not None:
                 self._worker.on_stored = self._remote.push     # upload what this worker stores
         try:
-            publish_ipc(self._engine_id, self._engine, t0.device.index or 0)   # peers may pull from us
-            self._pdw = PDWorker(self._engine, self._engine_id, self._block_size)
+            tp_rank = self._tp_rank()
+            publish_ipc(self._engine_id, self._engine, t0.device.index or 0, tp_rank, self._world)   # peers may pull from us
+            self._pdw = PDWorker(self._engine, self._engine_id, self._block_size, rank=tp_rank, tp_size=self._world)
         except Exception as e:  # e.g. VMM-allocated cache (sleep mode): P/D pull unavailable, offload still works
             logger.warning("b200kv: cannot publish CUDA-IPC descriptors (%s); peer pull disabled", e)
         if self.cfg.enable_controller and self.cfg.controller_pull_url and rank == 0:
@@ -262,6 +276,14 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                 include_partial=not self._discard_partial, heartbeat_s=self.cfg.worker_heartbeat_s,
                 ip=self.cfg.advertise_ip)
         logger.info("b200kv registered %d layers, %d blocks, stride %d", len(tensors), nb, stride)
+
+    def _tp_rank(self) -> int:
+        """This worker's tensor-parallel rank (every rank of an engine shares the engine id)."""
+        try:
+            from vllm.distributed.parallel_state import get_tensor_model_parallel_rank
+            return int(get_tensor_model_parallel_rank())
+        except Exception:
+            return int(getattr(self._vllm_config.parallel_config, "rank", 0) or 0) % max(self._world, 1)
 
     def _metas(self) -> list[ReqMeta]:
         md = self._get_connector_metadata()
@@ -324,7 +346,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             recv = self._worker.poll_async_loads() or None    # detached pool loads that have landed
         sent = None
         if self._pdw is not None:
-            sent, _pulled = self._pdw.poll()   # P/D pulls are synchronous for the scheduler
+            sent, _pulled = self._pdw.poll(block=True)   # P/D pulls are synchronous for the scheduler
             sent = sent or None
         return sent, recv
 
@@ -379,8 +401,10 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             self._controller.close()
             self._controller = None
         if self._pdw is not None:
-            unpublish_ipc(self._engine_id)
+            unpublish_ipc(self._engine_id, self._pdw.rank)
             self._pdw = None
+        if self._pd is not None:
+            self._pd.close()
         if self._worker is not None and self._worker.tiers is not None:
             if self._worker.local_tier is not None:
                 self._worker.local_tier.close()
@@ -407,12 +431,15 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         if remote is not None:   # decode side of a disaggregated request: pull from the prefiller
             self._remote_computed[request.request_id] = num_computed_tokens
             return remote, False
+        # multimodal items, cache_salt, LoRA adapter and lmcache.tag.* enter the chunk keys (adapter :1168-1172)
+        ident = self._sched.identities.get(request.request_id) or request_identity(request)
+        prompt = request.prompt_token_ids or []
         if self._remote is not None and self._remote.prefetch_state(
-                request.request_id, request.prompt_token_ids or []) == self._remote.PENDING:
+                request.request_id, prompt if ident is None else ident.apply(prompt)) == self._remote.PENDING:
             return None, False   # chunks are on their way from the cache server: ask again next step
-        n = self._sched.num_new_matched_tokens(request.request_id, request.prompt_token_ids or [],
+        n = self._sched.num_new_matched_tokens(request.request_id, prompt,
                                                request.num_tokens, num_computed_tokens,
-                                               int(getattr(request, "priority", 0) or 0))
+                                               int(getattr(request, "priority", 0) or 0), identity=ident)
         return n, bool(self._sched.async_load and n > 0)
 
     @_traced

@@ -220,6 +220,13 @@ class KVPool:
     def unlink(name: str):
         lib().b200kv_pool_unlink(name.encode())
 
+    @staticmethod
+    def sweep(prefix: str, min_age_s: int = 60) -> int:
+        """Unlink the segments /dev/shm/<prefix>* that no live process holds (b200kv_pool_sweep)."""
+        n = C.c_int32(0)
+        check(lib().b200kv_pool_sweep(prefix.encode(), min_age_s, C.byref(n)), "b200kv_pool_sweep")
+        return n.value
+
     def __del__(self):  # pragma: no cover
         try:
             self.close()

@@ -15,6 +15,15 @@ class LMCacheConnectorV1Impl:
     def __init__(self, vllm_config, role, parent):
         self._parent = parent
         self._inner = B200KVConnector(vllm_config, role, getattr(parent, "_kv_cache_config", None))
+        # The wrapper hands update_state_after_alloc no block ids (lmcache_connector.py:253-262).  What needs
+        # them at allocation time is therefore declined on this route — disaggregated-prefill pulls and loads
+        # detached from the forward step — and such requests are served by the pool lookup or recomputed,
+        # instead of being promised tokens that have nowhere to land.
+        if self._inner._pd is not None:
+            self._inner._pd.blocks_known_at_alloc = False
+        if self._inner._sched is not None:
+            self._inner._sched.async_load = False
+        self._inner.cfg.async_load = False
 
     def _sync_meta(self):
         self._inner._connector_metadata = self._parent._connector_metadata

@@ -101,6 +101,32 @@ void CUDART_CB op_host_cb(void* p) {
   op->host_done.store(1, std::memory_order_release);
 }
 
+// Undoes what a store / load had taken when it leaves early (argument the table cannot hold, a failed
+// CUDA call): reserved-but-uncommitted pool slots are aborted (otherwise later stores of those keys see
+// -EEXIST until the stale-writer reclaim), pinned chunks are released (otherwise they can never be
+// evicted), and the op's events are destroyed.  The engine's streams are drained first, so no copy into
+// or out of those slots is still in flight.
+struct OpGuard {
+  b200kv_ctx* ctx;
+  cudaStream_t s[4];
+  std::unique_ptr<Op> op;
+  std::vector<uint64_t> reserved;   // store: keys reserved in the pool, not yet handed to the commit callback
+  bool cb_enqueued = false;         // the host callback owns commit / release from here on
+  bool armed = true;
+  OpGuard(b200kv_ctx* c, cudaStream_t a, cudaStream_t b, cudaStream_t d, cudaStream_t e) : ctx(c), s{a, b, d, e} {}
+  ~OpGuard() {
+    if (!armed || (!op && reserved.empty())) return;
+    for (cudaStream_t st : s) if (st) cudaStreamSynchronize(st);
+    cudaGetLastError();
+    if (!cb_enqueued) {
+      for (uint64_t k : reserved) b200kv_pool_abort(ctx_pool(), k);
+      if (op) for (uint64_t k : op->release_keys) b200kv_pool_release(ctx_pool(), k);
+    }
+    if (op) destroy_op_events(op.get());
+  }
+  b200kv_pool* ctx_pool() const;
+};
+
 struct Peer {
   bool valid = false;
   int device = -1;
@@ -210,13 +236,18 @@ struct b200kv_ctx {
   // bulk-kernel launch shape
   int S = 2, LAG = 1, ctas_per_sm = 1;  // swept on B200: profiles/sweep_r01.txt
   int fp8_threads = 256;                // B200KV_FP8_THREADS: CTA width of the FP8 store kernel
-  bool fp8_two_pass = false;            // B200KV_FP8_2PASS=1: smem-free two-pass store kernel (experimental)
+  bool fp8_two_pass = false;            // B200KV_FP8_2PASS=1: smem-free two-pass store kernel (experimental, slower)
+  int fp8_store_ver = 3;                // B200KV_FP8_STORE: 3 = persistent warp-specialised kernel (default), 1 = cluster kernel
+  void* d_tmaps = nullptr;              // one CUtensorMap per plane (NHD pages: strided [bs][D] boxes for the FP8 store)
+  std::string tmap_status = "not built";
   uint32_t piece_tokens = 0, pieces = 0, stage_bytes = 0;
 
   void* tier_base = nullptr;            // device chunk tier (b200kv_tier_create)
   uint32_t tier_slots = 0;
   std::vector<void*> tier_imports;      // peers' tiers opened over CUDA IPC
 };
+
+b200kv_pool* OpGuard::ctx_pool() const { return ctx->pool; }
 
 namespace {
 
@@ -480,8 +511,70 @@ int launch_copy_runs(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView&
   return launch_hnd_partial<MODE>(ctx, p, p.runs + n_full, static_cast<uint32_t>(n_partial), s);
 }
 
+// Persistent FP8 store (kv_fp8_store3_kernel) when every chunk of the batch is a sequence of whole, block-aligned
+// runs (the last possibly short).  Returns 1 if it launched, 0 if the batch is not eligible, < 0 on error.
+static int try_launch_fp8_store3(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv, uint32_t n_chunks,
+                                 uint32_t n_tokens, cudaStream_t s) {
+  const Geometry& g = ctx->g;
+  const uint32_t head_bytes = g.D * 2, rv = head_bytes >> 4;
+  const uint64_t unit_bytes = static_cast<uint64_t>(g.C) * head_bytes;
+  if (ctx->fp8_store_ver != 3 || g.elem != 2 || unit_bytes > kS3MaxUnitBytes || (head_bytes & 15) || rv == 0 ||
+      (kS3GroupThreads % rv) != 0 || (static_cast<uint64_t>(g.bs) * head_bytes) % 128 != 0 || g.C / g.bs > 32 * 8)
+    return 0;
+  const bool use_tmap = !g.hnd || env_int("B200KV_FP8_TMAP_HND", 0);
+  if (use_tmap && (!ctx->d_tmaps || ctx->tmap_status != "ok")) return 0;
+  const Run* runs = reinterpret_cast<const Run*>(tv.slot->host + tv.runs_off);
+  const uint32_t* offs = reinterpret_cast<const uint32_t*>(tv.slot->host + tv.offs_off);
+  for (uint32_t c = 0; c < n_chunks; ++c) {
+    const uint32_t base = c * g.C;
+    if (base >= n_tokens) return 0;
+    const uint32_t n_valid = std::min<uint32_t>(g.C, n_tokens - base);
+    const uint32_t nb = (n_valid + g.bs - 1) / g.bs;
+    if (offs[c + 1] - offs[c] != nb) return 0;
+    for (uint32_t j = 0; j < nb; ++j) {
+      const Run& r = runs[offs[c] + j];
+      if (r.b != static_cast<int32_t>(base + j * g.bs) || (static_cast<uint32_t>(r.a) % g.bs) != 0 ||
+          static_cast<uint32_t>(r.n) != std::min<uint32_t>(g.bs, n_valid - j * g.bs))
+        return 0;
+    }
+  }
+  Fp8Store3Params p{};
+  p.paged = local_side(ctx);
+  p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off);
+  p.chunk_run_off = reinterpret_cast<const uint32_t*>(dev_table + tv.offs_off);
+  p.chunk_addrs = reinterpret_cast<const uint64_t*>(dev_table + tv.addrs_off);
+  p.tmaps = use_tmap ? ctx->d_tmaps : nullptr;
+  p.n_chunks = n_chunks;
+  p.n_planes = g.planes;
+  p.chunk_tokens = g.C;
+  p.n_tokens = n_tokens;
+  p.n_heads = g.H;
+  p.head_bytes = head_bytes;
+  p.slab_q_bytes = g.slab_bytes;
+  p.scales_off = g.scales_off;
+  p.hnd = g.hnd ? 1u : 0u;
+  p.total_units = n_chunks * g.planes * g.H;
+  const size_t smem = static_cast<size_t>(kS3Stages) * unit_bytes;
+  static bool attr_set[8] = {false};
+  const int dev = ctx->cfg.device & 7;
+  if (!attr_set[dev]) {
+    CU_TRY(cudaFuncSetAttribute(kv_fp8_store3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Stages * kS3MaxUnitBytes));
+    attr_set[dev] = true;
+  }
+  const uint32_t grid = std::min<uint32_t>(p.total_units, static_cast<uint32_t>(ctx->sm_count));
+  if (grid == 0) return 1;
+  kv_fp8_store3_kernel<<<grid, kS3Threads, smem, s>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++ctx->stats.n_kernel_launches;
+  return 1;
+}
+
 int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
                      uint32_t n_chunks, uint32_t n_tokens, cudaStream_t s) {
+  {
+    const int rc3 = try_launch_fp8_store3(ctx, dev_table, tv, n_chunks, n_tokens, s);
+    if (rc3 != 0) return rc3 < 0 ? rc3 : B200KV_OK;
+  }
   Fp8StoreParams p{};
   p.paged = local_side(ctx);
   p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off);
@@ -827,6 +920,7 @@ static int engine_create_impl(const b200kv_engine_config* cfg, b200kv_pool* pool
   ctx->ctas_per_sm = cfg->ctas_per_sm > 0 ? cfg->ctas_per_sm : env_int("B200KV_CTAS_PER_SM", 1);
   ctx->fp8_threads = env_int("B200KV_FP8_THREADS", 256) == 512 ? 512 : 256;
   ctx->fp8_two_pass = env_int("B200KV_FP8_2PASS", 0) != 0;
+  ctx->fp8_store_ver = env_int("B200KV_FP8_STORE", 3);
   const uint32_t stage_max = static_cast<uint32_t>(env_int("B200KV_STAGE_KB", 32)) << 10;
   if (g.token_bytes > stage_max || stage_max > kStageMax * 2) return B200KV_ENOTSUP;
   ctx->piece_tokens = std::min<uint32_t>(g.bs, stage_max / g.token_bytes);
@@ -923,10 +1017,68 @@ extern "C" int b200kv_engine_destroy(b200kv_ctx* ctx) {
   for (void* m : ctx->tier_imports) cudaIpcCloseMemHandle(m);
   if (ctx->tier_base) cudaFree(ctx->tier_base);
   if (ctx->d_bases) cudaFree(ctx->d_bases);
+  if (ctx->d_tmaps) cudaFree(ctx->d_tmaps);
   for (cudaStream_t s : {ctx->s_gather, ctx->s_d2h, ctx->s_h2d, ctx->s_scatter})
     if (s) cudaStreamDestroy(s);
   delete ctx;
   return B200KV_OK;
+}
+
+// One 4-D tensor map per plane over the paged cache, so that TMA can fetch "the bs rows of head h in block b"
+// — a [bs][D] box whose rows are a token apart — as ONE copy (SASS UTMALDG).  Dimensions are ordered by
+// ascending stride: NHD pages {D, H, bs, NB} (box {D, 1, bs, 1}), HND pages {D, bs, H, NB} (box {D, bs, 1, 1});
+// the box always lands as [bs][D] in shared memory.  Failure is not fatal: the FP8 store then runs its
+// cluster kernel.
+static void build_tensor_maps(b200kv_ctx* ctx, const std::vector<uint64_t>& bases) {
+  const Geometry& g = ctx->g;
+  if (ctx->cfg.format != B200KV_FMT_FP8 || g.elem != 2) { ctx->tmap_status = "not needed"; return; }
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+      q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    ctx->tmap_status = "cuTensorMapEncodeTiled unavailable";
+    return;
+  }
+  if (g.D > 256 || g.bs > 256) { ctx->tmap_status = "box too large"; return; }
+  std::vector<CUtensorMap> maps(g.planes);
+  const cuuint64_t row = static_cast<cuuint64_t>(g.D) * g.elem, tok = g.token_bytes, blk = ctx->cfg.block_stride_bytes;
+  for (uint32_t pl = 0; pl < g.planes; ++pl) {
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    dims[0] = g.D;
+    dims[3] = ctx->cfg.n_blocks;
+    if (g.hnd) { dims[1] = g.bs; dims[2] = g.H; strides[0] = row; strides[1] = row * g.bs; box[1] = g.bs; box[2] = 1; }
+    else       { dims[1] = g.H; dims[2] = g.bs; strides[0] = row; strides[1] = tok;        box[1] = 1; box[2] = g.bs; }
+    strides[2] = blk;
+    box[0] = g.D;
+    box[3] = 1;
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_UINT16, 4,
+                                                      reinterpret_cast<void*>(bases[pl]), dims, strides, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ctx->tmap_status = "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")";
+      return;
+    }
+  }
+  if (!ctx->d_tmaps && cudaMalloc(&ctx->d_tmaps, sizeof(CUtensorMap) * g.planes) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->d_tmaps = nullptr;
+    ctx->tmap_status = "cudaMalloc failed";
+    return;
+  }
+  if (cudaMemcpy(ctx->d_tmaps, maps.data(), sizeof(CUtensorMap) * g.planes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(ctx->d_tmaps);
+    ctx->d_tmaps = nullptr;
+    ctx->tmap_status = "cudaMemcpy failed";
+    return;
+  }
+  ctx->tmap_status = "ok";
 }
 
 extern "C" int b200kv_register_kv(b200kv_ctx* ctx, const void* const* k_ptrs,
@@ -945,6 +1097,8 @@ extern "C" int b200kv_register_kv(b200kv_ctx* ctx, const void* const* k_ptrs,
     h[2 * l + 1] = v;
   }
   CU_TRY(cudaMemcpy(ctx->d_bases, h.data(), sizeof(uint64_t) * h.size(), cudaMemcpyHostToDevice));
+  build_tensor_maps(ctx, h);
+  if (env_int("B200KV_VERBOSE", 0)) std::fprintf(stderr, "b200kv: tensor maps: %s\n", ctx->tmap_status.c_str());
   ctx->kv_registered = true;
   return B200KV_OK;
 }
@@ -1100,18 +1254,20 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
   // 1. reserve pool slots; chunks already present (or not placeable) are skipped
   struct Todo { int32_t c; uint32_t slot; uint32_t n_tok; };
   std::vector<Todo> todo;
+  OpGuard guard(ctx, ctx->s_gather, ctx->s_d2h, nullptr, nullptr);   // undoes the reservations on any early return
   for (int32_t c = 0; c < n_chunks; ++c) {
     const uint32_t n_tok = static_cast<uint32_t>(std::min<int64_t>(g.C, n_tokens - static_cast<int64_t>(c) * g.C));
     uint32_t slot = 0;
     const int rc = b200kv_pool_reserve(ctx->pool, keys[c], static_cast<int32_t>(n_tok), pool_fmt(ctx),
                                        ctx->cfg.owner, &slot);
-    if (rc == B200KV_OK) todo.push_back({c, slot, n_tok});
+    if (rc == B200KV_OK) { todo.push_back({c, slot, n_tok}); guard.reserved.push_back(keys[c]); }
     else if (rc != B200KV_EEXIST && rc != B200KV_ENOSPC) return rc;
   }
   ++ctx->stats.n_store_ops;
   if (todo.empty()) return B200KV_OK;
 
-  std::unique_ptr<Op> op(new Op());
+  guard.op.reset(new Op());
+  Op* op = guard.op.get();
   op->id = ctx->next_ticket++;
   op->pool = ctx->pool;
   CU_TRY(cudaEventCreateWithFlags(&op->done, cudaEventDisableTiming));
@@ -1185,10 +1341,13 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       ctx->stats.n_stored_tokens += t.n_tok;
     }
   }
-  CU_TRY(cudaLaunchHostFunc(ctx->s_d2h, op_host_cb, op.get()));
+  // chunks whose D2H was never queued (none on this path) would stay reserved: every todo chunk is in commit_keys
+  CU_TRY(cudaLaunchHostFunc(ctx->s_d2h, op_host_cb, op));
+  guard.cb_enqueued = true;
   CU_TRY(cudaEventRecord(op->done, ctx->s_d2h));
   *ticket = op->id;
-  ctx->ops.emplace(op->id, std::move(op));
+  ctx->ops.emplace(op->id, std::move(guard.op));
+  guard.armed = false;
   return B200KV_OK;
 }
 
@@ -1231,12 +1390,14 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
   ++ctx->stats.n_load_ops;
   if (todo.empty()) return B200KV_OK;
 
-  std::unique_ptr<Op> op(new Op());
+  OpGuard guard(ctx, ctx->s_h2d, ctx->s_scatter, nullptr, nullptr);
+  guard.op.reset(new Op());
+  Op* op = guard.op.get();
   op->id = ctx->next_ticket++;
   op->pool = ctx->pool;
   for (const Todo& t : todo) op->release_keys.push_back(keys[t.c]);
-  // From here on every exit path must run the release callback; errors below are CUDA failures
-  // (fatal for the engine), so the pins are dropped by the caller destroying the engine.
+  // From here on every early return drops the pins and the op's events through `guard` (not every failure
+  // below is fatal: table_acquire refuses an op whose run table does not fit).
   CU_TRY(cudaEventCreateWithFlags(&op->done, cudaEventDisableTiming));
 
   const bool detached = compute_stream == B200KV_STREAM_DETACHED;
@@ -1387,14 +1548,16 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
     }
     CU_TRY(cudaEventRecord(tv.slot->done_ev, ctx->s_scatter));
   }
-  CU_TRY(cudaLaunchHostFunc(ctx->s_scatter, op_host_cb, op.get()));
+  CU_TRY(cudaLaunchHostFunc(ctx->s_scatter, op_host_cb, op));
+  guard.cb_enqueued = true;
   CU_TRY(cudaEventRecord(op->done, ctx->s_scatter));
   // chunk-wise: the forward pass must see the loaded pages; layer-wise: it waits per layer instead
   if (!detached && !layerwise) CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));
   ctx->stats.n_loaded_tokens += loaded;
   if (n_loaded_tokens) *n_loaded_tokens = loaded;
   *ticket = op->id;
-  ctx->ops.emplace(op->id, std::move(op));
+  ctx->ops.emplace(op->id, std::move(guard.op));
+  guard.armed = false;
   return B200KV_OK;
 }
 

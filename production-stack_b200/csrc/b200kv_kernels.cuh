@@ -573,6 +573,186 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
 }
 
 // ---------------------------------------------------------------------------------------------
+// FP8 store, persistent warp-specialised pipeline (the default for block-structured ops).
+//
+// Unit of work = (chunk, plane, head): the C x D bf16 elements one scale covers (64 KiB for C=256,
+// D=128), i.e. exactly what has to be seen before anything can be quantised.  Nothing is exchanged
+// between CTAs: no cluster, no DSMEM, no atomics.  One CTA per SM:
+//   warp 0           producer: for every unit one TMA copy per paged block ([bs][D] of head h, 4 KiB) into
+//                    a kS3Stages-deep ring of unit buffers, completion on the stage's `full` mbarrier.
+//                    HND tiles: the piece is contiguous -> cp.async.bulk (UBLKCP).  NHD tiles: the piece is
+//                    bs rows of D elements strided by the token size -> cp.async.bulk.tensor.4d through a
+//                    per-plane tensor map {D, H, bs, NB}, box {D, 1, bs, 1} (UTMALDG).  Either way the unit
+//                    lands as [C tokens][D] in shared memory.
+//   2 x 8 warps      two consumer groups ping-pong over the units: wait `full`, copy the unit into registers
+//                    (16 x 16 B per thread, conflict-free), release the stage at once (`empty`), absmax
+//                    (packed u16 max, one REDUX per warp, one named barrier per group), quantise from
+//                    registers, 8-byte stores that fill whole 128-byte lines.
+// While one group reduces and quantises, the other group's loads and two more stages are in flight, so the
+// memory pipe never drains between the load -> absmax -> quantise phases of a unit (the cluster kernel above
+// runs at 33 % warps active with exactly that bubble).  HBM is read once and written once.
+// Eligibility (checked on the host, else the cluster kernel runs): every chunk is a sequence of whole,
+// block-aligned runs, the last one possibly short — what any vLLM block table produces.
+// ---------------------------------------------------------------------------------------------
+constexpr int kS3Stages = 3;
+constexpr int kS3Groups = 2;
+constexpr int kS3GroupThreads = 256;
+constexpr int kS3Threads = 32 + kS3Groups * kS3GroupThreads;
+constexpr int kS3MaxVec = 16;          // 16-byte vectors per consumer thread per unit
+constexpr uint32_t kS3MaxUnitBytes = kS3MaxVec * kS3GroupThreads * 16;   // 64 KiB
+
+struct Fp8Store3Params {
+  PagedSide paged;
+  const Run* runs;                // run j of chunk c = paged block j of the chunk (host-checked)
+  const uint32_t* chunk_run_off;  // [n_chunks+1]
+  const uint64_t* chunk_addrs;    // [n_chunks]
+  const void* tmaps;              // device array of CUtensorMap, one per plane (NHD); nullptr: plain bulk copies (HND)
+  uint32_t n_chunks, n_planes;
+  uint32_t chunk_tokens, n_tokens;
+  uint32_t n_heads, head_bytes;   // H, D*2
+  uint64_t slab_q_bytes, scales_off;
+  uint32_t hnd;
+  uint32_t total_units;           // n_chunks * n_planes * H
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 4-D tiled TMA load global -> shared (this CTA), completion on an mbarrier.  SASS: UTMALDG.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int32_t c0, int32_t c1, int32_t c2,
+                                            int32_t c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+__global__ void __maxnreg__(120) kv_fp8_store3_kernel(const Fp8Store3Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kS3Stages];
+  __shared__ __align__(8) uint64_t empty_bar[kS3Stages];
+  __shared__ uint32_t s_max[kS3Groups][2][kS3GroupThreads / 32];
+
+  const uint32_t bs = p.paged.block_tokens;
+  const uint32_t piece_bytes = bs * p.head_bytes;            // one block's rows of one head
+  const uint32_t unit_bytes = p.chunk_tokens * p.head_bytes;  // stage size (<= 64 KiB, host-checked)
+  const uint32_t H = p.n_heads;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kS3Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kS3GroupThreads / 32);   // one arrive per warp of the consuming group
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const uint32_t n_mine = p.total_units > blockIdx.x ? (p.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x < 32) {
+    // ------------------------------- producer -------------------------------
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = 0; i < n_mine; ++i) {
+      const uint32_t u = blockIdx.x + i * gridDim.x;
+      const uint32_t h = u % H;
+      const uint32_t plane = (u / H) % p.n_planes;
+      const uint32_t c = u / (H * p.n_planes);
+      const uint32_t s = i % kS3Stages, k = i / kS3Stages;
+      const uint32_t r0 = __ldg(p.chunk_run_off + c), r1 = __ldg(p.chunk_run_off + c + 1);
+      const uint32_t n_blocks = r1 - r0;
+      if (k > 0) mbar_wait(&empty_bar[s], (k - 1) & 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], n_blocks * piece_bytes);
+      __syncwarp();
+      uint8_t* stage = smem + static_cast<size_t>(s) * unit_bytes;
+      for (uint32_t j = lane; j < n_blocks; j += 32) {
+        const uint32_t block = static_cast<uint32_t>(p.runs[r0 + j].a) / bs;
+        uint8_t* dst = stage + static_cast<size_t>(j) * piece_bytes;
+        if (p.tmaps) {
+          const uint8_t* tm = static_cast<const uint8_t*>(p.tmaps) + static_cast<size_t>(plane) * 128;
+          if (p.hnd) tma_load_4d(dst, tm, 0, 0, static_cast<int32_t>(h), static_cast<int32_t>(block), &full_bar[s]);
+          else tma_load_4d(dst, tm, 0, static_cast<int32_t>(h), 0, static_cast<int32_t>(block), &full_bar[s]);
+        } else {
+          const uint64_t src = __ldg(p.paged.bases + plane) + static_cast<uint64_t>(block) * p.paged.block_stride +
+                               static_cast<uint64_t>(h) * piece_bytes;   // HND tile [H][bs][D]
+          bulk_g2s(dst, reinterpret_cast<const void*>(src), piece_bytes, &full_bar[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------- consumers -------------------------------
+  const uint32_t g = (threadIdx.x - 32) / kS3GroupThreads;
+  const uint32_t t = (threadIdx.x - 32) % kS3GroupThreads;
+  const uint32_t warp = t >> 5, lane = t & 31u;
+  const uint32_t rv = p.head_bytes >> 4;          // 16-byte vectors per (token, head) row; power of two (host-checked)
+  const uint32_t col8 = (t % rv) * 8;             // byte offset of this thread's 8 output bytes inside a row
+  const uint32_t tok0 = t / rv;                   // token of vector kk = tok0 + kk * tok_step
+  const uint32_t tok_step = kS3GroupThreads / rv;
+  const uint32_t out_row = p.head_bytes >> 1;     // D bytes of e4m3 per (token, head)
+  uint32_t it = 0;
+  for (uint32_t i = g; i < n_mine; i += kS3Groups, ++it) {
+    const uint32_t u = blockIdx.x + i * gridDim.x;
+    const uint32_t h = u % H;
+    const uint32_t plane = (u / H) % p.n_planes;
+    const uint32_t c = u / (H * p.n_planes);
+    const uint32_t s = i % kS3Stages, k = i / kS3Stages;
+    const uint32_t n_valid = min(p.chunk_tokens, p.n_tokens - c * p.chunk_tokens);
+    const uint8_t* stage = smem + static_cast<size_t>(s) * unit_bytes;
+
+    mbar_wait(&full_bar[s], k & 1);
+    uint4 x[kS3MaxVec];
+    uint32_t acc = 0;
+#pragma unroll
+    for (int kk = 0; kk < kS3MaxVec; ++kk) {
+      const uint32_t tok = tok0 + kk * tok_step;
+      if (tok < n_valid) {
+        x[kk] = *reinterpret_cast<const uint4*>(stage + (static_cast<size_t>(kk) * kS3GroupThreads + t) * 16);
+        acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(acc, x[kk].x), x[kk].y), x[kk].z), x[kk].w);
+      } else {
+        x[kk] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);    // the unit lives in registers now: the stage can be refilled
+
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, max(acc & 0xffffu, acc >> 16));
+    const uint32_t par = it & 1;
+    if (lane == 0) s_max[g][par][warp] = wmax;
+    named_bar_sync(1 + g, kS3GroupThreads);
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < kS3GroupThreads / 32; ++w) m = max(m, s_max[g][par][w]);
+    const float amax = __uint_as_float(m << 16);
+    const float inv = (m == 0) ? 1.0f : __fdiv_rn(448.0f, amax);
+    const uint64_t chunk_base = __ldg(p.chunk_addrs + c);
+    if (t == 0) {
+      float* scales = reinterpret_cast<float*>(chunk_base + p.scales_off);
+      scales[plane * H + h] = (m == 0) ? 1.0f : __fdiv_rn(amax, 448.0f);
+    }
+    uint8_t* slab = reinterpret_cast<uint8_t*>(chunk_base + static_cast<uint64_t>(plane) * p.slab_q_bytes);
+#pragma unroll
+    for (int kk = 0; kk < kS3MaxVec; ++kk) {
+      const uint32_t tok = tok0 + kk * tok_step;
+      if (tok < n_valid) {
+        size_t off;
+        if (p.hnd) {   // packed slab mirrors the tiles: [tile][H][bs][D]
+          const uint32_t tile = tok / bs, row = tok - tile * bs;
+          off = (static_cast<size_t>(tile * H + h) * bs + row) * out_row + col8;
+        } else {       // [token][H][D]
+          off = (static_cast<size_t>(tok) * H + h) * out_row + col8;
+        }
+        st_na_v2(slab + off, quant8(x[kk], inv));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP8 store, two-pass variant (B200KV_FP8_2PASS=1; experimental): same grid, cluster and output as
 // kv_fp8_store_kernel, but no shared-memory staging.  Pass 1 streams the CTA's window straight from
 // the pages into the per-head absmax; after the cluster exchange pass 2 reads the same bytes again —
@@ -838,8 +1018,18 @@ __device__ __forceinline__ uint64_t q4_src_addr(const Q4Params& p, uint32_t plan
   return paged_addr_hnd(p.paged, plane, slot, h, p.head_bytes) + static_cast<uint64_t>(c) * 16;
 }
 
+constexpr int kQ4Unroll = 4;   // 16-byte vectors a thread keeps in flight (the kernels are pure streaming)
+
+__device__ __forceinline__ void q4_split(uint32_t idx, uint32_t vpt, uint32_t vpt_shift, uint32_t* t, uint32_t* v) {
+  if (vpt_shift != 0xffffffffu) { *t = idx >> vpt_shift; *v = idx & (vpt - 1); }
+  else { *t = idx / vpt; *v = idx - *t * vpt; }
+}
+
+// q = clamp(rint(x * inv), -7, 7), inv = fl32(1 / s), s = bf16(absmax_group / 7)  (oracle/kv_oracle.py q4_pack_chunk):
+// one IEEE division per group, then multiplications.
 __global__ void __launch_bounds__(256) kv_q4_store_kernel(const Q4Params p) {
   const uint32_t vpt = (p.n_heads * p.head_bytes) >> 4;      // vectors per token (multiple of 4)
+  const uint32_t vpt_shift = (vpt & (vpt - 1)) == 0 ? 31u - __clz(vpt) : 0xffffffffu;
   const uint32_t codes_bytes = vpt * 4;
   for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x) {
     const uint32_t plane = p.plane_begin + ui % p.n_planes;
@@ -848,38 +1038,49 @@ __global__ void __launch_bounds__(256) kv_q4_store_kernel(const Q4Params p) {
     const uint32_t t0 = static_cast<uint32_t>(run.b) - c * p.chunk_tokens;
     uint8_t* slab = reinterpret_cast<uint8_t*>(__ldg(p.chunk_addrs + c) + static_cast<uint64_t>(plane) * p.slab_bytes);
     const uint32_t nvec = static_cast<uint32_t>(run.n) * vpt;
-    for (uint32_t base = 0; base < nvec; base += 256) {   // uniform trip count: every lane takes part in the shuffles
-      const uint32_t idx = base + threadIdx.x;             // 256 and vpt are multiples of 4: quads stay whole
-      const bool ok = idx < nvec;
-      const uint32_t t = ok ? idx / vpt : 0, v = ok ? idx - t * vpt : 0;
-      const uint4 x = ok ? ld_nc_v4(reinterpret_cast<const void*>(q4_src_addr(p, plane, static_cast<uint32_t>(run.a) + t, v)))
-                         : make_uint4(0, 0, 0, 0);
-      uint32_t acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(0u, x.x), x.y), x.z), x.w);
-      uint32_t m = max(acc & 0xffffu, acc >> 16);
-      m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-      m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-      const float amax = __uint_as_float(m << 16);
-      const __nv_bfloat16 sb = m ? __float2bfloat16_rn(__fdiv_rn(amax, 7.0f)) : __float2bfloat16_rn(1.0f);
-      const float s = __bfloat162float(sb);
-      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-      uint32_t packed = 0;
+    for (uint32_t base = 0; base < nvec; base += 256 * kQ4Unroll) {   // uniform trip count: every lane shuffles
+      uint4 x[kQ4Unroll];
+      uint32_t tt[kQ4Unroll], vv[kQ4Unroll];
+      bool ok[kQ4Unroll];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
-        const int ql = max(-7, min(7, __float2int_rn(__fdiv_rn(lo, s))));
-        const int qh = max(-7, min(7, __float2int_rn(__fdiv_rn(hi, s))));
-        packed |= (static_cast<uint32_t>(ql & 0xF) | (static_cast<uint32_t>(qh & 0xF) << 4)) << (8 * i);
+      for (int j = 0; j < kQ4Unroll; ++j) {                 // all loads first: kQ4Unroll x 16 B in flight per thread
+        const uint32_t idx = base + j * 256 + threadIdx.x;   // 256 and vpt are multiples of 4: quads stay whole
+        ok[j] = idx < nvec;
+        tt[j] = vv[j] = 0;
+        if (ok[j]) q4_split(idx, vpt, vpt_shift, &tt[j], &vv[j]);
+        x[j] = ok[j] ? ld_nc_v4(reinterpret_cast<const void*>(q4_src_addr(p, plane, static_cast<uint32_t>(run.a) + tt[j], vv[j])))
+                     : make_uint4(0, 0, 0, 0);
       }
-      if (!ok) continue;
-      uint8_t* rec = slab + static_cast<uint64_t>(t0 + t) * p.rec_bytes;
-      *reinterpret_cast<uint32_t*>(rec + static_cast<size_t>(v) * 4) = packed;
-      if ((v & 3u) == 0) *reinterpret_cast<__nv_bfloat16*>(rec + codes_bytes + static_cast<size_t>(v >> 2) * 2) = sb;
+#pragma unroll
+      for (int j = 0; j < kQ4Unroll; ++j) {
+        uint32_t acc = absmax_u16x2(absmax_u16x2(absmax_u16x2(absmax_u16x2(0u, x[j].x), x[j].y), x[j].z), x[j].w);
+        uint32_t m = max(acc & 0xffffu, acc >> 16);
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        const float amax = __uint_as_float(m << 16);
+        const __nv_bfloat16 sb = m ? __float2bfloat16_rn(__fdiv_rn(amax, 7.0f)) : __float2bfloat16_rn(1.0f);
+        const float inv = __fdiv_rn(1.0f, __bfloat162float(sb));
+        const uint32_t w[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+          const int ql = max(-7, min(7, __float2int_rn(__fmul_rn(lo, inv))));
+          const int qh = max(-7, min(7, __float2int_rn(__fmul_rn(hi, inv))));
+          packed |= (static_cast<uint32_t>(ql & 0xF) | (static_cast<uint32_t>(qh & 0xF) << 4)) << (8 * i);
+        }
+        if (!ok[j]) continue;
+        uint8_t* rec = slab + static_cast<uint64_t>(t0 + tt[j]) * p.rec_bytes;
+        *reinterpret_cast<uint32_t*>(rec + static_cast<size_t>(vv[j]) * 4) = packed;
+        if ((vv[j] & 3u) == 0) *reinterpret_cast<__nv_bfloat16*>(rec + codes_bytes + static_cast<size_t>(vv[j] >> 2) * 2) = sb;
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(256) kv_q4_load_kernel(const Q4Params p) {
   const uint32_t vpt = (p.n_heads * p.head_bytes) >> 4;
+  const uint32_t vpt_shift = (vpt & (vpt - 1)) == 0 ? 31u - __clz(vpt) : 0xffffffffu;
   const uint32_t codes_bytes = vpt * 4;
   for (uint32_t ui = blockIdx.x; ui < p.total_units; ui += gridDim.x) {
     const uint32_t plane = p.plane_begin + ui % p.n_planes;
@@ -889,21 +1090,37 @@ __global__ void __launch_bounds__(256) kv_q4_load_kernel(const Q4Params p) {
     const uint8_t* slab =
         reinterpret_cast<const uint8_t*>(__ldg(p.chunk_addrs + c) + static_cast<uint64_t>(plane) * p.slab_bytes);
     const uint32_t nvec = static_cast<uint32_t>(run.n) * vpt;
-    for (uint32_t idx = threadIdx.x; idx < nvec; idx += 256) {
-      const uint32_t t = idx / vpt, v = idx - t * vpt;
-      const uint8_t* rec = slab + static_cast<uint64_t>(t0 + t) * p.rec_bytes;
-      const uint32_t packed = *reinterpret_cast<const uint32_t*>(rec + static_cast<size_t>(v) * 4);
-      const float s = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rec + codes_bytes + static_cast<size_t>(v >> 2) * 2));
-      uint32_t o[4];
+    for (uint32_t base = threadIdx.x; base < nvec; base += 256 * kQ4Unroll) {
+      uint32_t packed[kQ4Unroll], tt[kQ4Unroll], vv[kQ4Unroll];
+      uint16_t sbits[kQ4Unroll];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int b = static_cast<int>((packed >> (8 * i)) & 0xffu);
-        const int ql = ((b & 0xF) ^ 8) - 8, qh = ((b >> 4) ^ 8) - 8;   // sign-extend the nibbles
-        const __nv_bfloat162 r = __floats2bfloat162_rn(static_cast<float>(ql) * s, static_cast<float>(qh) * s);
-        o[i] = *reinterpret_cast<const uint32_t*>(&r);
+      for (int j = 0; j < kQ4Unroll; ++j) {                 // all loads first
+        const uint32_t idx = base + j * 256;
+        packed[j] = 0;
+        sbits[j] = 0;
+        tt[j] = vv[j] = 0;
+        if (idx < nvec) {
+          q4_split(idx, vpt, vpt_shift, &tt[j], &vv[j]);
+          const uint8_t* rec = slab + static_cast<uint64_t>(t0 + tt[j]) * p.rec_bytes;
+          packed[j] = __ldg(reinterpret_cast<const uint32_t*>(rec + static_cast<size_t>(vv[j]) * 4));
+          sbits[j] = __ldg(reinterpret_cast<const uint16_t*>(rec + codes_bytes + static_cast<size_t>(vv[j] >> 2) * 2));
+        }
       }
-      st_na_v4(reinterpret_cast<void*>(q4_src_addr(p, plane, static_cast<uint32_t>(run.a) + t, v)),
-               make_uint4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+      for (int j = 0; j < kQ4Unroll; ++j) {
+        if (base + j * 256 >= nvec) continue;
+        const float s = __uint_as_float(static_cast<uint32_t>(sbits[j]) << 16);
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int b = static_cast<int>((packed[j] >> (8 * i)) & 0xffu);
+          const int ql = ((b & 0xF) ^ 8) - 8, qh = ((b >> 4) ^ 8) - 8;   // sign-extend the nibbles
+          const __nv_bfloat162 r = __floats2bfloat162_rn(static_cast<float>(ql) * s, static_cast<float>(qh) * s);
+          o[i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+        st_na_v4(reinterpret_cast<void*>(q4_src_addr(p, plane, static_cast<uint32_t>(run.a) + tt[j], vv[j])),
+                 make_uint4(o[0], o[1], o[2], o[3]));
+      }
     }
   }
 }

@@ -15,7 +15,9 @@
 #include <cstring>
 #include <new>
 
+#include <dirent.h>
 #include <fcntl.h>
+#include <sys/file.h>
 #include <pthread.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -91,6 +93,11 @@ struct b200kv_pool {
   uint64_t map_bytes = 0;
   bool creator = false;
   char name[256] = {0};
+  // Named segments: every process that has the pool open holds a shared flock on the segment's file for as
+  // long as it lives (the kernel drops it when the process dies, however it dies).  b200kv_pool_sweep()
+  // removes segments nobody holds: what a SIGKILLed / OOM-killed engine left behind in /dev/shm.
+  int lock_fd = -1;
+  ~b200kv_pool() { if (lock_fd >= 0) close(lock_fd); }
 
   uint64_t stale_ns = 120ull * 1000000000ull;  // B200KV_POOL_STALE_MS
   uint64_t die_key = 0;  // fault injection (tests): _exit inside the critical section of reserve(die_key)
@@ -340,19 +347,21 @@ extern "C" int b200kv_pool_open(const b200kv_pool_config* cfg, b200kv_pool** out
         return -e;
       }
     }
+    flock(fd, LOCK_SH);
+    p->lock_fd = fd;      // stays open (and locked) until b200kv_pool_close / process exit
   } else {
     creating = true;
   }
 
   if (creating) {
     if (cfg->slot_bytes == 0 || cfg->slot_bytes % 16 || cfg->pool_bytes < cfg->slot_bytes) {
-      if (fd >= 0) { close(fd); shm_unlink(cfg->shm_name); }
+      if (fd >= 0) shm_unlink(cfg->shm_name);
       delete p;
       return B200KV_EINVAL;
     }
     const uint64_t n_slots64 = cfg->pool_bytes / cfg->slot_bytes;
     if (n_slots64 > 0x7fffffffu) {
-      if (fd >= 0) { close(fd); shm_unlink(cfg->shm_name); }
+      if (fd >= 0) shm_unlink(cfg->shm_name);
       delete p;
       return B200KV_EINVAL;
     }
@@ -367,13 +376,11 @@ extern "C" int b200kv_pool_open(const b200kv_pool_config* cfg, b200kv_pool** out
     if (fd >= 0) {
       if (ftruncate(fd, static_cast<off_t>(total)) != 0) {
         const int e = errno;
-        close(fd);
         shm_unlink(cfg->shm_name);
         delete p;
         return -e;
       }
       m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-      close(fd);
     } else {
       m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     }
@@ -401,12 +408,10 @@ extern "C" int b200kv_pool_open(const b200kv_pool_config* cfg, b200kv_pool** out
       usleep(1000);
     }
     if (!size) {
-      close(fd);
       delete p;
       return B200KV_ENOENT;
     }
     void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-    close(fd);
     if (m == MAP_FAILED) {
       const int e = errno;
       delete p;
@@ -443,6 +448,32 @@ extern "C" int b200kv_pool_close(b200kv_pool* pool) {
   if (!pool) return B200KV_EINVAL;
   if (pool->h) munmap(pool->h, pool->map_bytes);
   delete pool;
+  return B200KV_OK;
+}
+
+extern "C" int b200kv_pool_sweep(const char* prefix, int32_t min_age_s, int32_t* n_removed) {
+  if (!prefix || !*prefix) return B200KV_EINVAL;
+  if (n_removed) *n_removed = 0;
+  const char* pfx = prefix[0] == '/' ? prefix + 1 : prefix;
+  DIR* d = opendir("/dev/shm");
+  if (!d) return -errno;
+  const size_t n = std::strlen(pfx);
+  const time_t now = time(nullptr);
+  while (dirent* e = readdir(d)) {
+    if (std::strncmp(e->d_name, pfx, n) != 0) continue;
+    char name[300];
+    std::snprintf(name, sizeof(name), "/%s", e->d_name);
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) continue;
+    struct stat st;
+    // young segments may belong to a creator that has not taken its lock yet
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && now - st.st_mtime >= min_age_s &&
+        flock(fd, LOCK_EX | LOCK_NB) == 0) {
+      if (shm_unlink(name) == 0 && n_removed) ++*n_removed;
+    }
+    close(fd);
+  }
+  closedir(d);
   return B200KV_OK;
 }
 

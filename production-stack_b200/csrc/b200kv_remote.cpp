@@ -162,11 +162,18 @@ struct b200kv_server {
     std::lock_guard<std::mutex> lk(mu);
     for (auto& p : pools)
       if (p.first == slot_bytes) return p.second;
-    if (pools.size() >= 16) return nullptr;
+    // B200KV_SERVER_GB is the budget of the whole server, not of each geometry: it is split evenly over the
+    // B200KV_SERVER_GEOMETRIES (default 1) chunk geometries the deployment serves, and a geometry beyond
+    // that number is refused (its PUTs fail, the engines treat the server as a miss) — a client cannot
+    // make the server allocate a pool per slot size it invents.
+    const char* ge = getenv("B200KV_SERVER_GEOMETRIES");
+    const size_t max_geoms = ge && atoi(ge) > 0 ? static_cast<size_t>(atoi(ge)) : 1;
+    if (pools.size() >= max_geoms || pools.size() >= 16) return nullptr;
+    const uint64_t share = pool_bytes / max_geoms;
     b200kv_pool_config pc;
     memset(&pc, 0, sizeof(pc));
     pc.shm_name = nullptr;
-    pc.pool_bytes = pool_bytes < slot_bytes ? slot_bytes : pool_bytes;
+    pc.pool_bytes = share < slot_bytes ? slot_bytes : share;
     pc.slot_bytes = slot_bytes;
     pc.flags = B200KV_POOL_CREATE;
     b200kv_pool* np = nullptr;

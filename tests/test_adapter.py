@@ -359,3 +359,74 @@ def test_preempted_request_restarts_on_its_new_blocks():
     req.all_token_ids = prompt + [7]
     cached = NS(req_ids=["p"], new_block_ids=[None], resumed_req_ids=set(), all_token_ids={}, num_computed_tokens=[len(prompt)])
     assert sched.build_meta(sched_out(cached=cached, num_sched={"p": 1})) == []
+
+
+# ---- what besides the tokens decides the KV: multimodal items, cache_salt, LoRA, lmcache.tag.* ----------------
+def _mm(ident, offset, length):
+    return NS(identifier=ident, mm_position=NS(offset=offset, length=length))
+
+
+def test_multimodal_items_enter_the_chunk_keys_like_the_reference_placeholder_rewrite():
+    """adapter :198, :344-350, :1168-1172: same text + different image must not share KV after the image;
+    chunks wholly BEFORE the placeholder are still shared (causal attention)."""
+    from b200kv import chunk_keys
+    from b200kv.adapter import request_identity
+    prompt = list(range(100, 100 + 4 * C))
+    req_a = NS(request_id="a", prompt_token_ids=prompt, mm_features=[_mm("deadbeef" * 8, 2 * C + 5, 20)])
+    req_b = NS(request_id="b", prompt_token_ids=prompt, mm_features=[_mm("0badf00d" * 8, 2 * C + 5, 20)])
+    req_a2 = NS(request_id="a2", prompt_token_ids=prompt, mm_features=[_mm("deadbeef" * 8, 2 * C + 5, 20)])
+    ka, kb, ka2 = (chunk_keys(request_identity(r).apply(prompt), C, 7) for r in (req_a, req_b, req_a2))
+    assert list(ka) == list(ka2)
+    assert list(ka[:2]) == list(kb[:2]) == list(chunk_keys(prompt, C, 7)[:2])     # before the image: shared, = plain text
+    assert ka[2] != kb[2] and ka[3] != kb[3]                                         # from the image on: distinct
+    assert request_identity(NS(request_id="t", prompt_token_ids=prompt)) is None    # plain text: untouched
+    # the window form used for decode-time tokens agrees with the whole-sequence form
+    ident = request_identity(req_a)
+    whole = ident.apply(prompt)
+    assert np.array_equal(ident.apply(prompt[2 * C:3 * C], start=2 * C), whole[2 * C:3 * C])
+
+
+def test_cache_salt_lora_and_tags_isolate_requests():
+    from b200kv.adapter import request_identity
+    prompt = list(range(3 * C))
+    plain = np.asarray(prompt, dtype=np.int32)
+    seen = [plain.tobytes()]
+    for kw in (dict(cache_salt="tenant-a"), dict(cache_salt="tenant-b"), dict(lora_request=NS(lora_name="adapter-1", lora_int_id=1)),
+               dict(sampling_params=NS(extra_args={"kv_transfer_params": {"lmcache.tag.user": "u1"}})),
+               dict(sampling_params=NS(extra_args={"kv_transfer_params": {"lmcache.tag.user": "u2"}}))):
+        ident = request_identity(NS(request_id="r", prompt_token_ids=prompt, **kw))
+        assert ident is not None and ident.salt
+        kt = ident.apply(prompt)
+        assert kt.dtype == np.int32 and (kt >= 0).all() and kt.tobytes() not in seen
+        seen.append(kt.tobytes())
+    # lmcache.skip_save alone is a save rule, not an identity
+    assert request_identity(NS(request_id="r", prompt_token_ids=prompt,
+                               sampling_params=NS(extra_args={"kv_transfer_params": {"lmcache.skip_save": True}}))) is None
+
+
+def test_scheduler_and_worker_use_key_tokens_end_to_end():
+    """Image A stored; same text with image B misses from the placeholder's chunk on; with image A again: full hit."""
+    from b200kv.adapter import request_identity
+    rng = np.random.default_rng(3)
+    layers = [rng.integers(0, 2 ** 16, (2, 64, BS, 2, 8), dtype=np.uint16) for _ in range(2)]
+    eng = OracleBackedEngine(layers)
+    sched = SchedulerState(lambda toks: eng.oe.lookup(toks), BS, C, discard_partial_chunks=False)
+    worker = WorkerState(eng, BS, C)
+    prompt = list(rng.integers(0, 1000, 3 * C))
+    feat_a, feat_b = [_mm("aa" * 32, C + 3, 10)], [_mm("bb" * 32, C + 3, 10)]
+
+    def turn(rid, feats, blocks):
+        req = NS(request_id=rid, prompt_token_ids=prompt, num_tokens=len(prompt), all_token_ids=prompt, mm_features=feats)
+        need = sched.num_new_matched_tokens(rid, prompt, len(prompt), 0, identity=request_identity(req))
+        sched.after_alloc(req, need)
+        nr = new_req(rid, prompt, blocks, computed=need)
+        metas = sched.build_meta(sched_out([nr], num_sched={rid: len(prompt) - need}))
+        worker.start_load(metas)
+        worker.save(metas)
+        sched.build_meta(sched_out(finished=[rid]))
+        return need
+
+    assert turn("a", feat_a, list(range(0, 12))) == 0
+    assert turn("b", feat_b, list(range(12, 24))) == C            # only the chunk before the image is reusable
+    assert turn("a2", feat_a, list(range(24, 36))) == 3 * C - 1   # full hit minus the recomputed last token
+    assert not sched.identities                                    # dropped with the finished requests

@@ -76,7 +76,7 @@ def test_scheduler_role_lookup_and_metadata(monkeypatch):
         assert conn.request_finished_all_groups(req, ([],)) == (False, None)
     finally:
         conn.shutdown()
-        KVPool.unlink("/b200kv-" + eid)
+        KVPool.unlink("/b200kv-eng-" + eid)
 
 
 def test_config_surface_uses_reference_env_names():
@@ -151,6 +151,13 @@ def test_vllm_builtin_lmcache_wrapper_drives_this_engine(monkeypatch):
         meta = conn.build_connector_meta(so)
         assert meta.requests[0].load_spec.can_load and meta.requests[0].load_spec.external_cached_tokens == 128
         assert conn.request_finished(req, []) == (False, None)
+        # the wrapper passes update_state_after_alloc no block ids: what would need them is declined on this
+        # route (a remote prefill is then an ordinary request: pool lookup / recompute), loads stay in-step
+        assert inner._pd.blocks_known_at_alloc is False and inner._sched.async_load is False
+        pd_req = NS(request_id="r2", prompt_token_ids=prompt, num_tokens=200, all_token_ids=prompt,
+                    kv_transfer_params={"do_remote_prefill": True, "remote_engine_id": "P", "remote_block_ids": [[1, 2, 3]],
+                                        "remote_num_tokens": 200})
+        assert conn.get_num_new_matched_tokens(pd_req, 0) == (128, False)      # the pool's answer, not 199 "remote" tokens
     finally:
         inner.shutdown()
         KVPool.unlink(inner._pool_name)
@@ -266,7 +273,7 @@ def test_shared_pool_name_is_per_geometry(monkeypatch):
     cfg = B200KVConfig(pool_name="box")
     assert pool_name_for(None, cfg, 0x2000000) == "/box-2000000"
     assert pool_name_for(None, cfg, 0x1000800) == "/box-1000800"
-    assert pool_name_for(NS(kv_transfer_config=NS(engine_id="e-1/x")), B200KVConfig(), 123) == "/b200kv-e-1x"
+    assert pool_name_for(NS(kv_transfer_config=NS(engine_id="e-1/x")), B200KVConfig(), 123) == "/b200kv-eng-e-1x"
 
 
 @pytest.mark.parametrize("backend,layout", [("flashinfer", "HND"), ("flashinfer", "NHD"), ("flash_attn", "NHD"),

@@ -43,12 +43,15 @@ class OracleEngine:
     instances = []
 
     def __init__(self, geom, pool, device=0, staging_bytes=0, owner=0, variant=0, stages=0, ctas_per_sm=0,
-                 key_seed=None):
+                 key_seed=None, numa_policy=0):
         self.geom, self.pool, self.owner = geom, pool, owner
         self.key_seed = geom.key_seed() if key_seed is None else key_seed
         self.oe = ko.OracleEngine(geom.chunk_tokens)
         self.calls = []
         OracleEngine.instances.append(self)
+
+    def numa_placement(self):
+        return "stand-in"
 
     def register_kv_caches(self, tensors, layout=None):
         self.layers = [t.view(torch.int16).numpy().view(np.uint16) for t in tensors]   # share memory

@@ -583,6 +583,7 @@ def test_fp8_two_pass_store_equals_default_kernel(monkeypatch, hnd, n_tok):
         sm = ko.slot_mapping_from_blocks(rng.permutation(p["NB"])[: (n_tok + p["bs"] - 1) // p["bs"]], p["bs"], n_tok)
     n_chunks = (n_tok + p["C"] - 1) // p["C"]
     out = []
+    monkeypatch.setenv("B200KV_FP8_STORE", "1")       # compare the two cluster kernels (the default is kernel 3)
     for two_pass in ("0", "1"):
         monkeypatch.setenv("B200KV_FP8_2PASS", two_pass)
         eng = KVEngine(geom, None, 0, staging_bytes=0)
@@ -593,3 +594,82 @@ def test_fp8_two_pass_store_equals_default_kernel(monkeypatch, hnd, n_tok):
         out.append(buf.cpu().numpy())
         eng.close()
     assert np.array_equal(out[0], out[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# The default FP8 store is the persistent warp-specialised kernel (kv_fp8_store3_kernel; TMA tensor maps on
+# NHD pages, bulk copies on HND pages); ops it does not take (token-granular mappings) run the cluster
+# kernel.  Both must produce the same chunk, byte for byte, and the tests above hold whichever runs
+# against the oracle.  Geometries: the test one (H=8, D=128), D=64, and Llama-3-8B's 32 layers.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hnd", [False, True])
+@pytest.mark.parametrize("shape", [(3, 8, 128, 96), (2, 4, 64, 96), (32, 8, 128, 160)])
+@pytest.mark.parametrize("n_tok", [1, 16, 17, 255, 256, 257, 700, 1024, 2048])
+def test_fp8_persistent_store_equals_cluster_kernel_and_oracle(monkeypatch, hnd, shape, n_tok):
+    need_gpu()
+    L, H, D, NB = shape
+    bs, C_ = 16, 256
+    if n_tok > NB * bs or (L == 32 and n_tok not in (257, 2048)):
+        pytest.skip("more tokens than pages / full-depth model checked at two sizes only")
+    rng = np.random.default_rng(9100 + n_tok + L)
+    host = mk_host_layers(rng, L, NB, bs, H, D)
+    dev = to_dev_hnd(host) if hnd else to_dev(host)
+    geom = KVGeometry(L, H, D, NB, bs, C_, 2, 2 * bs * H * D * 2 if hnd else 0, FMT_FP8,
+                      b200kv._lib.LAYOUT_HND if hnd else b200kv._lib.LAYOUT_NHD)
+    sm = ko.slot_mapping_from_blocks(rng.permutation(NB)[: (n_tok + bs - 1) // bs], bs, n_tok)
+    n_chunks = (n_tok + C_ - 1) // C_
+    out, launches = [], []
+    for ver in ("3", "1"):
+        monkeypatch.setenv("B200KV_FP8_STORE", ver)
+        eng = KVEngine(geom, None, 0, staging_bytes=0)
+        eng.register_kv_caches(dev)
+        buf = torch.zeros(n_chunks * geom.chunk_bytes, dtype=torch.uint8, device="cuda:0")
+        eng.gather(sm, buf.data_ptr())
+        torch.cuda.synchronize()
+        out.append(buf.cpu().numpy())
+        eng.close()
+    if not np.array_equal(out[0], out[1]):
+        bad = np.flatnonzero(out[0] != out[1])
+        pytest.fail(f"{len(bad)} bytes differ, first at {bad[:8]} (chunk bytes {geom.chunk_bytes}, scales at {geom.chunk_bytes - 2 * L * H * 4})")
+    if not hnd and L <= 3:      # and directly against the C oracle (NHD chunk layout)
+        want, cb, so = oracle_c.gather(host, sm, C_, "fp8")
+        got = out[0]
+        for c in range(n_chunks):
+            n = min(C_, n_tok - c * C_)
+            for plane in range(2 * L):
+                o = c * cb + plane * C_ * H * D
+                assert np.array_equal(got[o:o + n * H * D], want[o:o + n * H * D]), (c, plane)
+            assert np.array_equal(got[c * cb + so:c * cb + so + 2 * L * H * 4], want[c * cb + so:c * cb + so + 2 * L * H * 4])
+
+
+def test_refused_op_leaves_no_reserved_slots_and_no_pins():
+    """An op whose run table does not fit (token-granular mapping over hundreds of chunks) is refused with
+    -EINVAL *after* pool slots were reserved / chunks pinned: nothing may stay reserved (later stores of the
+    same keys would see -EEXIST until the stale-writer reclaim) or pinned (could never be evicted)."""
+    need_gpu()
+    L, NB, bs, H, D, C_ = 1, 8192, 16, 1, 64, 256
+    geom = KVGeometry(L, H, D, NB, bs, C_, 2, 0, FMT_RAW)
+    dev = [torch.randn((2, NB, bs, H, D), device="cuda:0").bfloat16() for _ in range(L)]
+    n_chunks = 420
+    pool = KVPool(None, (n_chunks + 8) * geom.chunk_bytes, geom.chunk_bytes, 1)
+    eng = KVEngine(geom, pool, 0, staging_bytes=2 * 512 * geom.chunk_bytes)    # one batch holds the whole op
+    eng.register_kv_caches(dev)
+    n = n_chunks * C_
+    rng = np.random.default_rng(11)
+    toks = rng.integers(0, 50000, n).astype(np.int32)
+    scattered = (np.arange(n, dtype=np.int64) * 2) % (NB * bs) + (np.arange(n) * 2 // (NB * bs))   # no two neighbours adjacent
+    assert len(np.unique(scattered)) == n
+    with pytest.raises(b200kv.B200KVError) as ei:
+        eng.store(toks, None, scattered)                    # > 87 381 runs: the table refuses it
+    assert ei.value.code == b200kv._lib.EINVAL
+    st = pool.stats()
+    assert st["n_used"] == 0 and pool.check(), st             # every reservation was aborted
+    # the same keys can be stored right away (block-structured mapping now), and loaded
+    sm = ko.slot_mapping_from_blocks(rng.permutation(NB)[: n // bs], bs, n)
+    eng.wait(eng.store(toks, None, sm))
+    assert pool.stats()["n_stored_chunks"] == n_chunks and eng.lookup(toks) == n
+    with pytest.raises(b200kv.B200KVError):
+        eng.retrieve(toks, None, scattered)                 # refused after pinning 420 chunks ...
+    assert pool.clear()                                      # ... none of which stayed pinned (clear() fails with pins)
+    eng.close()
+    pool.close()

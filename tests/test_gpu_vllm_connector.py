@@ -49,7 +49,7 @@ def _run(connector: str, fmt: str, compiled: bool, tmp_path, extra_env=None):
         import glob
         segs = glob.glob("/dev/shm" + pool + "*")
         assert segs, "the engine never created its pool segment"
-        kp = KVPool("/" + os.path.basename(segs[0]), 0, 0, 0)     # attach only
+        kp = KVPool("/" + os.path.basename(segs[0]), 0, 0, 2)     # POOL_ATTACH
         res["pool"] = kp.stats()
         kp.close()
         return res

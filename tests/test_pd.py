@@ -113,3 +113,92 @@ def test_lease_expiry_and_failures(shm):
     d_sched.after_alloc(d_req, [7, 8, 9], n, 0)
     work.start_pulls(d_sched.build_meta())
     assert work.take_failed_blocks() == {7, 8, 9} and eng.pulls == []
+
+
+class WaitableEngine(FakeEngine):
+    def wait(self, ticket):
+        self.done.add(ticket)
+
+
+def _prefill(shm, eid="P3", lease_s=60.0, tp=1):
+    eng = FakeEngine()
+    pd.publish_ipc(eid, eng, device=0, rank=0, tp_size=tp)
+    sched = pd.PDScheduler(eid, BS, lease_s=lease_s, tp_size=tp)
+    req = NS(request_id="p-req", prompt_token_ids=list(range(64)), num_computed_tokens=64,
+             kv_transfer_params={"do_remote_decode": True})
+    delay, params = sched.request_finished(req, [10, 11, 12, 13])
+    assert delay and params["remote_lease_id"] and params["tp_size"] == tp
+    assert os.path.exists(pd.lease_path(eid, params["remote_lease_id"]))
+    return sched, params
+
+
+def test_expired_lease_turns_a_pull_into_reported_load_errors(shm):
+    """The producer frees held blocks when its lease runs out; a consumer that pulls later (or is still
+    pulling) must report its blocks for recompute, not decode on recycled pages."""
+    sched, params = _prefill(shm)
+    d_eng = WaitableEngine()
+    d_sched, d_work = pd.PDScheduler("D3", BS), pd.PDWorker(d_eng, "D3", BS)
+    d_req = NS(request_id="d-req", prompt_token_ids=list(range(64)), kv_transfer_params=dict(params))
+    n = d_sched.remote_prefill_tokens(d_req, 0)
+    d_sched.after_alloc(d_req, [1, 2, 3, 4], n, 0)
+    meta = d_sched.build_meta()
+    assert meta.pulls[0].remote_lease_id == params["remote_lease_id"]
+    # (a) lease gone while the pull is in flight: detected by the check AFTER the pull
+    d_work.start_pulls(meta)
+    assert len(d_eng.pulls) == 1 and d_work.take_failed_blocks() == set()
+    sched.sending_finished({"p-req"})                      # producer: lease expired -> file removed, blocks freed next
+    assert not os.path.exists(pd.lease_path("P3", params["remote_lease_id"]))
+    assert d_work.poll(block=True)[1] == {"d-req"}         # still reported as finished ...
+    assert d_work.take_failed_blocks() == {1, 2, 3, 4}     # ... with its blocks invalid
+    # (b) lease already gone before the pull starts: no pull is issued at all
+    d_work.start_pulls(meta)
+    assert len(d_eng.pulls) == 1 and d_work.take_failed_blocks() == {1, 2, 3, 4} and d_work.n_lease_failures == 2
+
+
+def test_live_lease_pull_is_clean_and_lease_removed_before_blocks_are_freed(shm):
+    sched, params = _prefill(shm, "P4")
+    d_eng = WaitableEngine()
+    d_sched, d_work = pd.PDScheduler("D4", BS), pd.PDWorker(d_eng, "D4", BS)
+    d_req = NS(request_id="d", prompt_token_ids=list(range(64)), kv_transfer_params=dict(params))
+    n = d_sched.remote_prefill_tokens(d_req, 0)
+    d_sched.after_alloc(d_req, [1, 2, 3, 4], n, 0)
+    d_work.start_pulls(d_sched.build_meta())
+    assert d_work.poll(block=True)[1] == {"d"} and d_work.take_failed_blocks() == set()
+    assert os.path.exists(os.path.join(pd.done_dir("P4"), "p-req"))
+    sched.sending_finished({"p-req"})
+    assert not os.path.exists(pd.lease_path("P4", params["remote_lease_id"]))
+
+
+def test_tensor_parallel_ranks_have_their_own_control_files_and_sizes_must_match(shm):
+    e0, e1 = FakeEngine(), FakeEngine()
+    p0 = pd.publish_ipc("PT", e0, device=0, rank=0, tp_size=2)
+    p1 = pd.publish_ipc("PT", e1, device=1, rank=1, tp_size=2)
+    assert p0 != p1 and os.path.isdir(pd.done_dir("PT", 0)) and os.path.isdir(pd.done_dir("PT", 1))
+    # decode rank 1 maps prefill rank 1's cache (device 1), not whoever wrote last
+    d1 = FakeEngine()
+    assert pd.PeerResolver(d1, rank=1, tp_size=2).resolve("PT") == 0 and d1.imported[1] == 1
+    d0 = FakeEngine()
+    assert pd.PeerResolver(d0, rank=0, tp_size=2).resolve("PT") == 0 and d0.imported[1] == 0
+    # a TP=1 decoder must not pull half of the heads from a TP=2 prefiller
+    with pytest.raises(ValueError):
+        pd.PeerResolver(FakeEngine(), rank=0, tp_size=1).resolve("PT")
+    sched1 = pd.PDScheduler("D", BS, tp_size=1)
+    req = NS(request_id="x", prompt_token_ids=list(range(40)),
+             kv_transfer_params={"do_remote_prefill": True, "remote_engine_id": "PT", "remote_block_ids": [[1, 2, 3]], "tp_size": 2})
+    assert sched1.remote_prefill_tokens(req, 0) is None
+    # each rank's marker releases that rank only
+    w0, w1 = pd.PDWorker(e0, "PT", BS, rank=0, tp_size=2), pd.PDWorker(e1, "PT", BS, rank=1, tp_size=2)
+    held = pd.PDMeta([], {"r": 1e18})
+    w0.start_pulls(held)
+    w1.start_pulls(held)
+    open(os.path.join(pd.done_dir("PT", 1), "r"), "w").close()
+    assert w0.poll()[0] == set() and w1.poll()[0] == {"r"}
+
+
+def test_fewer_local_blocks_than_promised_tokens_is_a_load_failure(shm):
+    _, params = _prefill(shm, "P5")
+    d_eng = WaitableEngine()
+    d_work = pd.PDWorker(d_eng, "D5", BS)
+    spec = pd.PullSpec("d", "P5", "p-req", [10, 11, 12, 13], [7], 63, remote_lease_id=params["remote_lease_id"])
+    d_work.start_pulls(pd.PDMeta([spec], {}))
+    assert d_eng.pulls == [] and d_work.take_failed_blocks() == {7}

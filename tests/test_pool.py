@@ -292,3 +292,43 @@ def test_named_pool_survives_engine_restart(shm_name):
     with pytest.raises(B200KVError):                                          # another model geometry: refused
         KVPool(shm_name, 4 * SLOT, 2 * SLOT, _lib.POOL_CREATE_OR_ATTACH)
     again.close()
+
+
+def test_sweep_removes_only_segments_nobody_holds():
+    """A per-engine segment whose processes died (SIGKILL: no atexit) is removed by the next engine's start-up
+    sweep; a segment somebody still has open — in this or another process — is left alone."""
+    import multiprocessing as mp
+    import os
+    import signal
+    import time
+    from b200kv import KVPool, _lib
+    tag = f"b200kv-swp{os.getpid()}-"
+    live, dead = "/" + tag + "live", "/" + tag + "dead"
+
+    def holder(name, ready):
+        import sys
+        sys.path[:0] = [os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "production-stack_b200")]
+        from b200kv import KVPool as KP, _lib as L
+        keep = KP(name, 4 * 4096, 4096, L.POOL_CREATE)   # noqa: F841  (the reference keeps the segment open, i.e. locked)
+        ready.set()
+        time.sleep(60)
+
+    ctx = mp.get_context("fork")
+    ready = ctx.Event()
+    p = ctx.Process(target=holder, args=(dead, ready))
+    p.start()
+    assert ready.wait(30)
+    mine = KVPool(live, 4 * 4096, 4096, _lib.POOL_CREATE)
+    try:
+        assert KVPool.sweep("/" + tag, 0) == 0                       # both held
+        os.kill(p.pid, signal.SIGKILL)
+        p.join(10)
+        assert os.path.exists("/dev/shm" + dead)                     # the killed process could not clean up
+        assert KVPool.sweep("/" + tag, 3600) == 0                    # too young for a cautious sweep
+        assert KVPool.sweep("/" + tag, 0) == 1
+        assert not os.path.exists("/dev/shm" + dead) and os.path.exists("/dev/shm" + live)
+        assert mine.check()
+    finally:
+        mine.close()
+        KVPool.unlink(live)
+        KVPool.unlink(dead)

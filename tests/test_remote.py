@@ -81,7 +81,17 @@ def test_put_get_roundtrip_is_bit_exact(server):
     c.close()
 
 
-def test_server_evicts_lru_and_keeps_one_pool_per_geometry(server):
+def test_server_evicts_lru_and_keeps_one_pool_per_geometry(monkeypatch):
+    # the server's budget (12 slots' worth) is split over the 2 geometries it is told to expect
+    monkeypatch.setenv("B200KV_SERVER_GEOMETRIES", "2")
+    server = RemoteServer("127.0.0.1", 0, 12 * SLOT)
+    try:
+        _geometry_checks(server)
+    finally:
+        server.stop()
+
+
+def _geometry_checks(server):
     a = mk_pool(16)
     c = RemoteClient("127.0.0.1", server.port)
     for k in range(1, 9):                                   # server holds 6 slots
@@ -106,6 +116,13 @@ def test_server_evicts_lru_and_keeps_one_pool_per_geometry(server):
     # asking for a chunk of the other geometry is refused (payload drained, connection still usable)
     assert c.get(other, 8, 0) == _lib.EINVAL and c.get(a, 77, 0) == _lib.EINVAL
     assert c.ping()
+    # a third slot size is not given a pool of its own (the budget is the server's, not each geometry's)
+    third = KVPool(None, 2 * 4 * SLOT, 4 * SLOT, _lib.POOL_CREATE)
+    slot = third.reserve(99, 256, 0, 0)
+    third.slot_view(slot)[:] = 1
+    third.commit(99)
+    assert c.put(third, 99, 0) != 0 and c.exists(np.array([99], np.uint64)) == 0
+    assert c.ping() and c.exists(np.array([77], np.uint64)) == 1
     c.close()
 
 
