@@ -18,6 +18,7 @@ across the scheduler->worker boundary); the slot mapping slot[i] = block[i//bs]*
 from __future__ import annotations
 
 import logging
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -358,6 +359,9 @@ class WorkerState:
         # device chunk tier (b200kv/device_tier.py): this engine's tier, and every tier it can read
         self.local_tier = None
         self.tiers = None
+        # operational kill-switch: while this file exists, loads bypass the device tiers (host pool / server only);
+        # lets one running deployment be measured with and without the NVLink path (tools/e2e/run_scale.py)
+        self.tier_disable_file: str | None = None
         self._tier_pins: list[tuple[object, list]] = []   # (event after the scatter, [(view, key)]) still pinned
         self.event_factory = None   # stream -> object with .query(); default torch.cuda.Event (tests inject one)
         self.stats = WorkerStats()
@@ -383,7 +387,8 @@ class WorkerState:
             t0 = time.perf_counter()
             try:
                 ret = None
-                if self.tiers is not None and not m.async_load:
+                if self.tiers is not None and not m.async_load and not (
+                        self.tier_disable_file and os.path.exists(self.tier_disable_file)):
                     ret = self._load_with_tiers(tokens, sm, masked, stream)   # None: no tier holds any of it
                 if ret is not None:
                     pass

@@ -250,6 +250,7 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             try:
                 n_slots = max(1, int(self.cfg.device_tier_gb * (1 << 30)) // geom.chunk_bytes)
                 self._worker.tiers = TierSet(self._engine_id, geom.chunk_bytes, fmt_tag, importer=self._engine.tier_import)
+                self._worker.tier_disable_file = os.environ.get("B200KV_TIER_DISABLE_FILE") or None
                 if self.kv_role != "kv_consumer":
                     self._worker.local_tier = LocalTier(self._engine, self._engine_id, n_slots, t0.device.index or 0,
                                                         fmt_tag, owner_tag_of(self.cfg.instance_id))

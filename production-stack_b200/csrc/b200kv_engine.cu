@@ -519,7 +519,8 @@ static int try_launch_fp8_store3(b200kv_ctx* ctx, const uint8_t* dev_table, cons
   const uint32_t head_bytes = g.D * 2, rv = head_bytes >> 4;
   const uint64_t unit_bytes = static_cast<uint64_t>(g.C) * head_bytes;
   if (ctx->fp8_store_ver != 3 || g.elem != 2 || unit_bytes > kS3MaxUnitBytes || (head_bytes & 15) || rv == 0 ||
-      (kS3GroupThreads % rv) != 0 || (static_cast<uint64_t>(g.bs) * head_bytes) % 128 != 0 || g.C / g.bs > 32 * 8)
+      (kS3GroupThreads % rv) != 0 || (static_cast<uint64_t>(g.bs) * head_bytes) % 128 != 0 || g.C / g.bs > 32 * 8 ||
+      (g.hnd && (kS3GroupThreads / rv) % g.bs != 0))
     return 0;
   const bool use_tmap = !g.hnd || env_int("B200KV_FP8_TMAP_HND", 0);
   if (use_tmap && (!ctx->d_tmaps || ctx->tmap_status != "ok")) return 0;

@@ -631,7 +631,7 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) 
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
-__global__ void __maxnreg__(120) kv_fp8_store3_kernel(const Fp8Store3Params p) {
+__global__ void __launch_bounds__(kS3Threads, 1) kv_fp8_store3_kernel(const Fp8Store3Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kS3Stages];
   __shared__ __align__(8) uint64_t empty_bar[kS3Stages];
@@ -735,19 +735,21 @@ __global__ void __maxnreg__(120) kv_fp8_store3_kernel(const Fp8Store3Params p) {
       scales[plane * H + h] = (m == 0) ? 1.0f : __fdiv_rn(amax, 448.0f);
     }
     uint8_t* slab = reinterpret_cast<uint8_t*>(chunk_base + static_cast<uint64_t>(plane) * p.slab_q_bytes);
+    // output offset of vector kk is linear in kk: NHD [token][H][D]; HND [tile][H][bs][D] when a step of
+    // tok_step tokens is a whole number of tiles (the host checks tok_step % bs == 0 before choosing this kernel)
+    uint32_t off0, off_step;
+    if (p.hnd) {
+      const uint32_t tile0 = tok0 / bs, row0 = tok0 - tile0 * bs;
+      off0 = ((tile0 * H + h) * bs + row0) * out_row + col8;
+      off_step = (tok_step / bs) * H * bs * out_row;
+    } else {
+      off0 = (tok0 * H + h) * out_row + col8;
+      off_step = tok_step * H * out_row;
+    }
+    uint8_t* dst = slab + off0;
 #pragma unroll
     for (int kk = 0; kk < kS3MaxVec; ++kk) {
-      const uint32_t tok = tok0 + kk * tok_step;
-      if (tok < n_valid) {
-        size_t off;
-        if (p.hnd) {   // packed slab mirrors the tiles: [tile][H][bs][D]
-          const uint32_t tile = tok / bs, row = tok - tile * bs;
-          off = (static_cast<size_t>(tile * H + h) * bs + row) * out_row + col8;
-        } else {       // [token][H][D]
-          off = (static_cast<size_t>(tok) * H + h) * out_row + col8;
-        }
-        st_na_v2(slab + off, quant8(x[kk], inv));
-      }
+      if (tok0 + kk * tok_step < n_valid) st_na_v2(dst + static_cast<size_t>(kk) * off_step, quant8(x[kk], inv));
     }
   }
 }

@@ -603,7 +603,7 @@ def test_fp8_two_pass_store_equals_default_kernel(monkeypatch, hnd, n_tok):
 # against the oracle.  Geometries: the test one (H=8, D=128), D=64, and Llama-3-8B's 32 layers.
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("hnd", [False, True])
-@pytest.mark.parametrize("shape", [(3, 8, 128, 96), (2, 4, 64, 96), (32, 8, 128, 160)])
+@pytest.mark.parametrize("shape", [(3, 8, 128, 96), (2, 4, 64, 96), (32, 8, 128, 160)], ids=["L3H8D128", "L2H4D64", "L32H8D128"])
 @pytest.mark.parametrize("n_tok", [1, 16, 17, 255, 256, 257, 700, 1024, 2048])
 def test_fp8_persistent_store_equals_cluster_kernel_and_oracle(monkeypatch, hnd, shape, n_tok):
     need_gpu()

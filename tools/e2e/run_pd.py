@@ -33,6 +33,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 from run_e2e import wait_ready  # noqa: E402
 
+MODEL = "synth-llama3-8b"     # served model name (tools/e2e/run_scale.py serves under the directory name)
+
 
 def start_server(gpu: int, port: int, model_dir: str, max_len: int, log_path: str, extra: list[str]):
     env = dict(os.environ)
@@ -79,7 +81,7 @@ async def drive(args, p_urls, d_urls):
 
 async def one_request(args, s, i, p_url, d_url):
     prompt = f"request {i} " + " ".join(["hi"] * args.prompt_words)
-    base = {"model": "synth-llama3-8b", "prompt": prompt, "max_tokens": args.max_tokens, "temperature": 0}
+    base = {"model": MODEL, "prompt": prompt, "max_tokens": args.max_tokens, "temperature": 0}
     # reference: one engine does everything (decode engine, no hand-off)
     ref_ttft, ref_text = await stream_completion(s, d_url + "/v1/completions", dict(base, stream=True))
     # step 1: prefill

@@ -9,10 +9,10 @@ timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_q4.py -m g
     -k "fp8 or q4 or refused or store_retrieve or layerwise" > "$out/pytest_kernels.txt" 2>&1
 tail -15 "$out/pytest_kernels.txt"
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider \
-    -k "persistent and (3-8-128-96 or 2-4-64-96) and (257 or 1024)" > "$out/sanitizer_memcheck.log" 2>&1
+    -k "persistent and (L3H8D128 or L2H4D64) and (257 or 1024)" > "$out/sanitizer_memcheck.log" 2>&1
 tail -3 "$out/sanitizer_memcheck.log"
 timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider \
-    -k "persistent and 3-8-128-96 and 257" > "$out/sanitizer_racecheck.log" 2>&1
+    -k "persistent and L3H8D128 and 257" > "$out/sanitizer_racecheck.log" 2>&1
 tail -3 "$out/sanitizer_racecheck.log"
 python tools/microbench.py --no-torch-baseline --out "$out/microbench.json" > "$out/microbench.log" 2>&1
 grep -E '"n_tok": 32768' "$out/microbench.log" | cut -c1-220
