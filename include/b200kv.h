@@ -274,6 +274,23 @@ int b200kv_load_layerwise_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n
                                 int64_t* n_loaded_tokens);
 int b200kv_wait_layer(b200kv_ctx* ctx, uint64_t ticket, int32_t layer, void* compute_stream);
 
+/* One engine step in ONE op.  The adapter calls lmcache_engine.store / .retrieve once per scheduled request
+ * (wait_for_save loop vllm_v1_adapter.py:1047-1128, start_load_kv loop :819-905) and moves the slot mapping
+ * to the GPU per call (:1072 "TODO pre-allocated buffer"); here the chunks of every request of the step are
+ * handed over together: one run table, one upload, one kernel launch per staging batch, one ticket.
+ * Chunk c holds chunk_tokens[c] (1..C) tokens whose slots are slot_mapping[c*C .. c*C + chunk_tokens[c]) —
+ * the caller lays the requests out back to back, each request's last chunk padded to C entries (padding is
+ * never read).  Store: chunks already present are skipped, as in b200kv_store_async.  Load: request r owns
+ * chunks [req_first_chunk[r], req_first_chunk[r+1]) and is loaded up to ITS first missing chunk;
+ * req_loaded_tokens[r] receives the tokens scheduled for it.  layers_per_group > 0 = layer-wise (see above). */
+int b200kv_store_batch_async(b200kv_ctx* ctx, const uint64_t* keys, const int32_t* chunk_tokens,
+                             int32_t n_chunks, const int64_t* slot_mapping, void* compute_stream,
+                             uint64_t* ticket);
+int b200kv_load_batch_async(b200kv_ctx* ctx, const uint64_t* keys, const int32_t* chunk_tokens,
+                            int32_t n_chunks, const int32_t* req_first_chunk, int32_t n_reqs,
+                            const int64_t* slot_mapping, int32_t layers_per_group, void* compute_stream,
+                            uint64_t* ticket, int64_t* req_loaded_tokens);
+
 int b200kv_poll(b200kv_ctx* ctx, uint64_t ticket, int* done);
 int b200kv_wait(b200kv_ctx* ctx, uint64_t ticket);
 int b200kv_wait_all(b200kv_ctx* ctx);

@@ -98,6 +98,8 @@ SIGNATURES = {
     "b200kv_load_async": (C.c_int, [_P, _U64P, C.c_int32, _I64P, C.c_int64, C.c_int32, _P, _U64P, _I64P]),
     "b200kv_load_layerwise_async": (C.c_int, [_P, _U64P, C.c_int32, _I64P, C.c_int64, C.c_int32, C.c_int32, _P, _U64P, _I64P]),
     "b200kv_wait_layer": (C.c_int, [_P, C.c_uint64, C.c_int32, _P]),
+    "b200kv_store_batch_async": (C.c_int, [_P, _U64P, _I32P, C.c_int32, _I64P, _P, _U64P]),
+    "b200kv_load_batch_async": (C.c_int, [_P, _U64P, _I32P, C.c_int32, _I32P, C.c_int32, _I64P, C.c_int32, _P, _U64P, _I64P]),
     "b200kv_poll": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int)]),
     "b200kv_wait": (C.c_int, [_P, C.c_uint64]),
     "b200kv_wait_all": (C.c_int, [_P]),

@@ -369,9 +369,12 @@ class WorkerState:
     def start_load(self, metas: list[ReqMeta], stream=None, layers_per_group: int = 0):
         """start_load_kv (adapter :798-905).  layers_per_group > 0 = LMCache's `use_layerwise`
         (:870-880): the load is issued layer group by layer group and the caller makes the forward
-        pass wait per layer (wait_for_layer_load)."""
+        pass wait per layer (wait_for_layer_load).  The requests of one step that load from the pinned pool are
+        handed to the engine together (KVEngine.retrieve_batch: one run table, one launch per staging batch)
+        instead of one engine call per request as the reference adapter's loop does."""
         import time
         self.layer_loads = []
+        plain = []      # (meta, tokens, sm, masked, n): pool loads that can share one engine op
         for m in metas:
             spec = m.load_spec
             if spec is None or not spec.can_load:
@@ -381,46 +384,76 @@ class WorkerState:
                 continue
             tokens = m.token_ids[:n]
             sm = m.slot_mapping(self.block_size)[:n]
-            mask = np.ones(n, dtype=bool)
             masked = spec.vllm_cached_tokens // self.chunk * self.chunk
-            mask[:masked] = False
             t0 = time.perf_counter()
             try:
                 ret = None
                 if self.tiers is not None and not m.async_load and not (
                         self.tier_disable_file and os.path.exists(self.tier_disable_file)):
                     ret = self._load_with_tiers(tokens, sm, masked, stream)   # None: no tier holds any of it
-                if ret is not None:
-                    pass
-                elif m.async_load:
+                if ret is None and not m.async_load:
+                    plain.append((m, tokens, sm, masked, n))
+                    continue
+                if ret is None:
+                    mask = np.ones(n, dtype=bool)
+                    mask[:masked] = False
                     ret, ticket = self.engine.retrieve(tokens, mask, sm, stream="detached", return_ticket=True)
                     self.async_loads.append((ticket, m.req_id))
-                elif layers_per_group > 0:
-                    ret, ticket = self.engine.retrieve(tokens, mask, sm, stream=stream, return_ticket=True,
-                                                       layers_per_group=layers_per_group)
-                    if ticket:
-                        self.layer_loads.append((ticket, m.block_ids[masked // self.block_size:
-                                                                   (n + self.block_size - 1) // self.block_size]))
-                else:
-                    ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
             except Exception as e:  # no exception on the data path (SURVEY §8b "Errors"): recompute instead
                 logger.error("b200kv: retrieve failed for %s: %s", m.req_id, e)
                 ret = np.zeros(n, dtype=bool)
                 if m.async_load:
                     self.async_loads.append((0, m.req_id))   # still has to be reported as finished
             self.stats.retrieve_seconds += time.perf_counter() - t0
-            self.stats.retrieve_calls += 1
-            got = int(ret.sum())
-            self.stats.num_loaded_tokens += got
-            if got and self.owner_tag:
-                self.stats.num_foreign_loaded_tokens += self._foreign_tokens(tokens, masked, masked + got)
-            if masked + got < n:
-                # short load: report the blocks vLLM believes are filled so it recomputes them
-                # (KVConnectorBase_V1.get_block_ids_with_load_errors, base.py:375-393)
-                self.stats.num_load_shortfalls += 1
-                first_bad = (masked + got) // self.block_size
-                last = (n + self.block_size - 1) // self.block_size
-                self.load_error_blocks.update(m.block_ids[first_bad:last])
+            self._account_load(m, tokens, masked, n, int(ret.sum()))
+        if not plain:
+            return
+        t0 = time.perf_counter()
+        if len(plain) > 1 and hasattr(self.engine, "retrieve_batch"):
+            try:
+                got, ticket = self.engine.retrieve_batch([(tokens, sm, masked) for _m, tokens, sm, masked, _n in plain],
+                                                         stream=stream, layers_per_group=layers_per_group)
+            except Exception as e:
+                logger.error("b200kv: batched retrieve of %d requests failed: %s", len(plain), e)
+                got, ticket = np.zeros(len(plain), dtype=np.int64), 0
+            if ticket and layers_per_group > 0:
+                blocks = []
+                for (m, _t, _s, masked, n), g_ in zip(plain, got):
+                    blocks += m.block_ids[masked // self.block_size:(masked + int(g_) + self.block_size - 1) // self.block_size]
+                self.layer_loads.append((ticket, blocks))
+            for (m, tokens, _sm, masked, n), g_ in zip(plain, got):
+                self._account_load(m, tokens, masked, n, int(g_))
+        else:
+            for m, tokens, sm, masked, n in plain:
+                mask = np.ones(n, dtype=bool)
+                mask[:masked] = False
+                try:
+                    if layers_per_group > 0:
+                        ret, ticket = self.engine.retrieve(tokens, mask, sm, stream=stream, return_ticket=True,
+                                                           layers_per_group=layers_per_group)
+                        if ticket:
+                            self.layer_loads.append((ticket, m.block_ids[masked // self.block_size:
+                                                                       (n + self.block_size - 1) // self.block_size]))
+                    else:
+                        ret = self.engine.retrieve(tokens, mask, sm, stream=stream)
+                except Exception as e:
+                    logger.error("b200kv: retrieve failed for %s: %s", m.req_id, e)
+                    ret = np.zeros(n, dtype=bool)
+                self._account_load(m, tokens, masked, n, int(ret.sum()))
+        self.stats.retrieve_seconds += time.perf_counter() - t0
+
+    def _account_load(self, m: ReqMeta, tokens, masked: int, n: int, got: int):
+        self.stats.retrieve_calls += 1
+        self.stats.num_loaded_tokens += got
+        if got and self.owner_tag:
+            self.stats.num_foreign_loaded_tokens += self._foreign_tokens(tokens, masked, masked + got)
+        if masked + got < n:
+            # short load: report the blocks vLLM believes are filled so it recomputes them
+            # (KVConnectorBase_V1.get_block_ids_with_load_errors, base.py:375-393)
+            self.stats.num_load_shortfalls += 1
+            first_bad = (masked + got) // self.block_size
+            last = (n + self.block_size - 1) // self.block_size
+            self.load_error_blocks.update(m.block_ids[first_bad:last])
 
     def _load_with_tiers(self, tokens, sm, masked: int, stream) -> np.ndarray:
         """Chunk by chunk from the nearest copy: a device tier (own, then a peer's: scatter straight from
@@ -501,6 +534,7 @@ class WorkerState:
         the caller's stream is made to wait for them, the D2H runs behind."""
         if self.kv_role == "kv_consumer":
             return
+        work = []     # (meta, tokens, sm, lead, n)
         for m in metas:
             ss = m.save_spec
             if ss is None or not ss.can_save:
@@ -512,31 +546,49 @@ class WorkerState:
             lead = ss.skip_leading_tokens // self.chunk * self.chunk
             if n <= lead:
                 continue
-            sm = m.slot_mapping(self.block_size)[:n]
-            mask = np.ones(n, dtype=bool)
-            mask[:lead] = False
+            work.append((m, tokens[:n], m.slot_mapping(self.block_size)[:n], lead, n))
+        if not work:
+            return
+        stored = [False] * len(work)
+        if len(work) > 1 and hasattr(self.engine, "store_batch"):
+            # every request of the step in ONE engine op (one table upload, one launch per staging batch)
             try:
-                ticket = self.engine.store(tokens[:n], mask, sm, offset=lead, stream=stream)
+                ticket = self.engine.store_batch([(t, sm, lead) for _m, t, sm, lead, _n in work], stream=stream)
+                if ticket:
+                    self.pending_tickets.append(ticket)
+                stored = [True] * len(work)
             except Exception as e:  # a failed store is a future miss, never a failed request
-                logger.error("b200kv: store failed for %s: %s", m.req_id, e)
+                logger.error("b200kv: batched store of %d requests failed: %s", len(work), e)
+        else:
+            for i, (m, t, sm, lead, n) in enumerate(work):
+                mask = np.ones(n, dtype=bool)
+                mask[:lead] = False
+                try:
+                    ticket = self.engine.store(t, mask, sm, offset=lead, stream=stream)
+                except Exception as e:
+                    logger.error("b200kv: store failed for %s: %s", m.req_id, e)
+                    continue
+                if ticket:
+                    self.pending_tickets.append(ticket)
+                stored[i] = True
+        for ok, (m, tokens, sm, lead, n) in zip(stored, work):
+            if not ok:
                 continue
-            if ticket:
-                self.pending_tickets.append(ticket)
             self.stats.num_stored_tokens += n - lead
             if self.on_stored is not None:
                 try:
-                    self.on_stored(self.engine._keys(tokens[:n])[lead // self.chunk:])
+                    self.on_stored(self.engine._keys(tokens)[lead // self.chunk:])
                 except Exception as e:
                     logger.error("b200kv: remote upload hook failed for %s: %s", m.req_id, e)
             if self.local_tier is not None:
                 try:
                     c0 = lead // self.chunk
-                    keys = self.engine._keys(tokens[:n])[c0:]
+                    keys = self.engine._keys(tokens)[c0:]
                     ct = np.minimum(self.chunk, n - (c0 + np.arange(len(keys))) * self.chunk).astype(np.int32)
                     self.local_tier.put(keys, ct, sm[lead:], self.chunk, stream)
                 except Exception as e:
                     logger.error("b200kv: device tier store failed for %s: %s", m.req_id, e)
-            ss.skip_leading_tokens = n
+            m.save_spec.skip_leading_tokens = n
 
     def wait_layer(self, layer: int, stream=None):
         for ticket, _blocks in self.layer_loads:

@@ -376,6 +376,70 @@ class KVEngine:
         ret[skip:skip + loaded.value] = True
         return (ret, ticket.value) if return_ticket else ret
 
+    # ---- one engine step in one op (b200kv_store_batch_async / b200kv_load_batch_async) -------------------
+    def _batch_layout(self, reqs):
+        """reqs: [(tokens, slot_mapping, first_chunk)] — chunks [first_chunk, ...) of each request take part.
+        -> (keys, chunk_tokens, req_first_chunk, padded slot mapping): requests back to back, every request's
+        last chunk padded to C entries."""
+        C_ = self.geom.chunk_tokens
+        keys, ct, first, sms = [], [], [0], []
+        for tokens, sm, c0 in reqs:
+            n = len(tokens)
+            k = self._keys(tokens)[c0:]
+            sm = _as_i64(sm)
+            if len(sm) != n:
+                raise ValueError("slot_mapping and tokens differ in length")
+            part = sm[c0 * C_:]
+            pad = len(k) * C_ - len(part)
+            sms.append(part if pad == 0 else np.concatenate([part, np.full(pad, -1, dtype=np.int64)]))
+            keys.append(k)
+            ct.append(np.minimum(C_, n - (c0 + np.arange(len(k))) * C_).astype(np.int32))
+            first.append(first[-1] + len(k))
+        return (np.ascontiguousarray(np.concatenate(keys), dtype=np.uint64), np.ascontiguousarray(np.concatenate(ct)),
+                np.asarray(first, dtype=np.int32), np.ascontiguousarray(np.concatenate(sms)))
+
+    def store_batch(self, reqs, stream=None) -> int:
+        """reqs: [(tokens, slot_mapping, offset)] with chunk-aligned offsets (tokens[offset:] are stored).  One
+        ticket for all of them; 0 if nothing was to do."""
+        C_ = self.geom.chunk_tokens
+        todo = []
+        for tokens, sm, offset in reqs:
+            if offset % C_:
+                raise ValueError("offset must be chunk aligned (adapter :1084-1088)")
+            if len(tokens) > offset:
+                todo.append((tokens, sm, offset // C_))
+        if not todo:
+            return 0
+        keys, ct, _first, sm = self._batch_layout(todo)
+        ticket = C.c_uint64(0)
+        check(lib().b200kv_store_batch_async(self._h, _ptr(keys, C.c_uint64), _ptr(ct, C.c_int32), len(keys),
+                                              _ptr(sm, C.c_int64), _stream_ptr(stream), C.byref(ticket)),
+              "b200kv_store_batch_async")
+        return ticket.value
+
+    def retrieve_batch(self, reqs, stream=None, layers_per_group: int = 0):
+        """reqs: [(tokens, slot_mapping, masked_tokens)] with chunk-aligned masked prefixes.  -> (tokens loaded
+        per request (after its masked prefix), ticket)."""
+        C_ = self.geom.chunk_tokens
+        todo = []
+        for tokens, sm, skip in reqs:
+            if skip % C_:
+                raise ValueError("masked prefix must be chunk aligned (adapter :848-854)")
+            todo.append((tokens, sm, skip // C_))
+        loaded = np.zeros(len(todo), dtype=np.int64)
+        live = [i for i, (tokens, _, c0) in enumerate(todo) if len(tokens) > c0 * C_]
+        if not live:
+            return loaded, 0
+        keys, ct, first, sm = self._batch_layout([todo[i] for i in live])
+        got = np.zeros(len(live), dtype=np.int64)
+        ticket = C.c_uint64(0)
+        check(lib().b200kv_load_batch_async(self._h, _ptr(keys, C.c_uint64), _ptr(ct, C.c_int32), len(keys),
+                                             _ptr(first, C.c_int32), len(live), _ptr(sm, C.c_int64), layers_per_group,
+                                             _stream_ptr(stream), C.byref(ticket), _ptr(got, C.c_int64)),
+              "b200kv_load_batch_async")
+        loaded[live] = got
+        return loaded, ticket.value
+
     def lookup(self, tokens, lease_ms: int = 0) -> int:
         if self.pool is None:
             return 0

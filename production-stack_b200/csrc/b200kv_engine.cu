@@ -296,7 +296,7 @@ int build_runs(const b200kv_ctx* ctx, const int64_t* slots, int64_t tok_begin, i
     const int64_t s = slots[i];
     if (s < 0 || s >= max_slot) return B200KV_EINVAL;
     const bool extend = cur.n > 0 && s == static_cast<int64_t>(cur.a) + cur.n && (s % g.bs) != 0 &&
-                        (i % g.C) != 0 && !(g.hnd && ((i - b_shift) % g.bs) == 0);
+                        ((i - b_shift) % g.C) != 0 && !(g.hnd && ((i - b_shift) % g.bs) == 0);
     if (extend) {
       ++cur.n;
     } else {
@@ -514,7 +514,7 @@ int launch_copy_runs(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView&
 // Persistent FP8 store (kv_fp8_store3_kernel) when every chunk of the batch is a sequence of whole, block-aligned
 // runs (the last possibly short).  Returns 1 if it launched, 0 if the batch is not eligible, < 0 on error.
 static int try_launch_fp8_store3(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv, uint32_t n_chunks,
-                                 uint32_t n_tokens, cudaStream_t s) {
+                                 const uint32_t* chunk_ntok, cudaStream_t s) {
   const Geometry& g = ctx->g;
   const uint32_t head_bytes = g.D * 2, rv = head_bytes >> 4;
   const uint64_t unit_bytes = static_cast<uint64_t>(g.C) * head_bytes;
@@ -528,8 +528,8 @@ static int try_launch_fp8_store3(b200kv_ctx* ctx, const uint8_t* dev_table, cons
   const uint32_t* offs = reinterpret_cast<const uint32_t*>(tv.slot->host + tv.offs_off);
   for (uint32_t c = 0; c < n_chunks; ++c) {
     const uint32_t base = c * g.C;
-    if (base >= n_tokens) return 0;
-    const uint32_t n_valid = std::min<uint32_t>(g.C, n_tokens - base);
+    const uint32_t n_valid = chunk_ntok[c];
+    if (n_valid == 0 || n_valid > g.C) return 0;
     const uint32_t nb = (n_valid + g.bs - 1) / g.bs;
     if (offs[c + 1] - offs[c] != nb) return 0;
     for (uint32_t j = 0; j < nb; ++j) {
@@ -548,7 +548,7 @@ static int try_launch_fp8_store3(b200kv_ctx* ctx, const uint8_t* dev_table, cons
   p.n_chunks = n_chunks;
   p.n_planes = g.planes;
   p.chunk_tokens = g.C;
-  p.n_tokens = n_tokens;
+  p.n_tokens = 0;   // unused: a chunk's token count comes from its runs
   p.n_heads = g.H;
   p.head_bytes = head_bytes;
   p.slab_q_bytes = g.slab_bytes;
@@ -570,12 +570,14 @@ static int try_launch_fp8_store3(b200kv_ctx* ctx, const uint8_t* dev_table, cons
   return 1;
 }
 
+// chunk_ntok[c] = tokens of chunk c of this launch (chunks of several requests may be partial anywhere)
 int launch_fp8_store(b200kv_ctx* ctx, const uint8_t* dev_table, const TableView& tv,
-                     uint32_t n_chunks, uint32_t n_tokens, cudaStream_t s) {
+                     uint32_t n_chunks, const uint32_t* chunk_ntok, cudaStream_t s) {
   {
-    const int rc3 = try_launch_fp8_store3(ctx, dev_table, tv, n_chunks, n_tokens, s);
+    const int rc3 = try_launch_fp8_store3(ctx, dev_table, tv, n_chunks, chunk_ntok, s);
     if (rc3 != 0) return rc3 < 0 ? rc3 : B200KV_OK;
   }
+  const uint32_t n_tokens = 0;  // unused by the kernels (see above)
   Fp8StoreParams p{};
   p.paged = local_side(ctx);
   p.runs = reinterpret_cast<const Run*>(dev_table + tv.runs_off);
@@ -1151,7 +1153,10 @@ static int gather_scatter(b200kv_ctx* ctx, const int64_t* slots, int64_t n_token
   rc = timing_begin(ctx, which, s);
   if (rc) return rc;
   if (ctx->cfg.format == B200KV_FMT_FP8) {
-    rc = is_gather ? launch_fp8_store(ctx, tv.slot->dev, tv, n_chunks, static_cast<uint32_t>(n_tokens), s)
+    std::vector<uint32_t> cn(n_chunks);
+    for (uint32_t c = 0; c < n_chunks; ++c)
+      cn[c] = static_cast<uint32_t>(std::min<int64_t>(g.C, n_tokens - static_cast<int64_t>(c) * g.C));
+    rc = is_gather ? launch_fp8_store(ctx, tv.slot->dev, tv, n_chunks, cn.data(), s)
                    : launch_fp8_load(ctx, tv.slot->dev, tv, 0, runs.size(), s);
   } else if (ctx->cfg.format == B200KV_FMT_Q4) {
     rc = launch_q4(ctx, is_gather, tv.slot->dev, tv, 0, runs.size(), s);
@@ -1232,13 +1237,15 @@ extern "C" int b200kv_tier_import(b200kv_ctx* ctx, const b200kv_ipc_desc* desc, 
 // ------------------------------------------------------------------------------------------------
 // store: paged HBM -> staging (kernel) -> pinned pool (DMA)
 // ------------------------------------------------------------------------------------------------
-extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
-                                  const int64_t* slot_mapping, int64_t n_tokens,
-                                  void* compute_stream, uint64_t* ticket) {
-  if (!ctx || !keys || !slot_mapping || n_tokens <= 0 || !ticket) return B200KV_EINVAL;
+// Chunk c of the op holds chunk_tokens[c] tokens whose slots are slot_mapping[c*C .. c*C + chunk_tokens[c]): a
+// single request (every chunk full but the last) or the chunks of SEVERAL requests back to back, each
+// request's tail padded to the chunk size (b200kv_store_batch_async: one table, one launch per staging
+// batch and one ticket for a whole engine step).
+static int store_impl(b200kv_ctx* ctx, const uint64_t* keys, const int32_t* chunk_tokens, int32_t n_chunks,
+                      const int64_t* slot_mapping, void* compute_stream, uint64_t* ticket) {
+  if (!ctx || !keys || !chunk_tokens || !slot_mapping || n_chunks <= 0 || !ticket) return B200KV_EINVAL;
   if (!ctx->pool || !ctx->kv_registered || ctx->stage.empty()) return B200KV_EINVAL;
   const Geometry& g = ctx->g;
-  if (n_chunks != static_cast<int32_t>((n_tokens + g.C - 1) / g.C)) return B200KV_EINVAL;
   DeviceGuard dg(ctx->cfg.device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   reap(ctx);
@@ -1249,15 +1256,19 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
   //    reserved-but-never-committed
   {
     const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
-    for (int64_t i = 0; i < n_tokens; ++i)
-      if (slot_mapping[i] < 0 || slot_mapping[i] >= max_slot) return B200KV_EINVAL;
+    for (int32_t c = 0; c < n_chunks; ++c) {
+      if (chunk_tokens[c] <= 0 || chunk_tokens[c] > static_cast<int32_t>(g.C)) return B200KV_EINVAL;
+      const int64_t* sm = slot_mapping + static_cast<int64_t>(c) * g.C;
+      for (int32_t i = 0; i < chunk_tokens[c]; ++i)
+        if (sm[i] < 0 || sm[i] >= max_slot) return B200KV_EINVAL;
+    }
   }
   // 1. reserve pool slots; chunks already present (or not placeable) are skipped
   struct Todo { int32_t c; uint32_t slot; uint32_t n_tok; };
   std::vector<Todo> todo;
   OpGuard guard(ctx, ctx->s_gather, ctx->s_d2h, nullptr, nullptr);   // undoes the reservations on any early return
   for (int32_t c = 0; c < n_chunks; ++c) {
-    const uint32_t n_tok = static_cast<uint32_t>(std::min<int64_t>(g.C, n_tokens - static_cast<int64_t>(c) * g.C));
+    const uint32_t n_tok = static_cast<uint32_t>(chunk_tokens[c]);
     uint32_t slot = 0;
     const int rc = b200kv_pool_reserve(ctx->pool, keys[c], static_cast<int32_t>(n_tok), pool_fmt(ctx),
                                        ctx->cfg.owner, &slot);
@@ -1286,10 +1297,10 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
     std::vector<Run> runs, partial;
     std::vector<uint32_t> offs(nb + 1);
     std::vector<uint64_t> addrs(nb);
-    std::vector<uint32_t> sidx(nb);
-    uint32_t batch_tokens = 0;
+    std::vector<uint32_t> sidx(nb), batch_ntok(nb);
     for (size_t i = 0; i < nb; ++i) {
       const Todo& t = todo[b0 + i];
+      batch_ntok[i] = t.n_tok;
       offs[i] = static_cast<uint32_t>(runs.size());
       const int64_t tb = static_cast<int64_t>(t.c) * g.C;
       // dense op-relative token index: chunk i of this batch starts at i*C
@@ -1300,7 +1311,6 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
       ctx->store_next = (ctx->store_next + 1) % static_cast<uint32_t>(n_stage);
       addrs[i] = reinterpret_cast<uint64_t>(ctx->d_staging) + static_cast<uint64_t>(sidx[i]) * g.chunk_bytes;
       if (ctx->stage[sidx[i]].used) CU_TRY(cudaStreamWaitEvent(ctx->s_gather, ctx->stage[sidx[i]].free_ev, 0));
-      batch_tokens = static_cast<uint32_t>(i) * g.C + t.n_tok;
     }
     offs[nb] = static_cast<uint32_t>(runs.size());
     const size_t n_full = runs.size(), n_part = partial.size();
@@ -1317,8 +1327,7 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
     rc = timing_begin(ctx, 0, ctx->s_gather);
     if (rc) return rc;
     if (ctx->cfg.format == B200KV_FMT_FP8) {
-      // a partial chunk is always the last of the op, hence the last of its batch
-      rc = launch_fp8_store(ctx, tv.slot->dev, tv, static_cast<uint32_t>(nb), batch_tokens, ctx->s_gather);
+      rc = launch_fp8_store(ctx, tv.slot->dev, tv, static_cast<uint32_t>(nb), batch_ntok.data(), ctx->s_gather);
     } else if (ctx->cfg.format == B200KV_FMT_Q4) {
       rc = launch_q4(ctx, true, tv.slot->dev, tv, 0, runs.size(), ctx->s_gather);
     } else {
@@ -1352,41 +1361,70 @@ extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t
   return B200KV_OK;
 }
 
+extern "C" int b200kv_store_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
+                                  const int64_t* slot_mapping, int64_t n_tokens,
+                                  void* compute_stream, uint64_t* ticket) {
+  if (!ctx || n_tokens <= 0) return B200KV_EINVAL;
+  const int64_t C = ctx->g.C;
+  if (n_chunks != static_cast<int32_t>((n_tokens + C - 1) / C)) return B200KV_EINVAL;
+  std::vector<int32_t> ct(static_cast<size_t>(n_chunks));
+  for (int32_t c = 0; c < n_chunks; ++c) ct[c] = static_cast<int32_t>(std::min<int64_t>(C, n_tokens - c * C));
+  return store_impl(ctx, keys, ct.data(), n_chunks, slot_mapping, compute_stream, ticket);
+}
+
+extern "C" int b200kv_store_batch_async(b200kv_ctx* ctx, const uint64_t* keys, const int32_t* chunk_tokens,
+                                        int32_t n_chunks, const int64_t* slot_mapping, void* compute_stream,
+                                        uint64_t* ticket) {
+  return store_impl(ctx, keys, chunk_tokens, n_chunks, slot_mapping, compute_stream, ticket);
+}
+
 // ------------------------------------------------------------------------------------------------
 // load: pinned pool -> staging (DMA) -> paged HBM (kernel), pipelined per chunk
 // ------------------------------------------------------------------------------------------------
-static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, const int64_t* slot_mapping,
-                     int64_t n_tokens, int32_t skip_chunks, void* compute_stream, uint64_t* ticket,
-                     int64_t* n_loaded_tokens, int32_t layers_per_group) {
-  if (!ctx || !keys || !slot_mapping || n_tokens <= 0 || !ticket || skip_chunks < 0 || layers_per_group < 0)
+// Chunk layout as in store_impl.  Request r owns chunks [req_first[r], req_first[r+1]); each request is loaded
+// up to its first missing chunk (prefix semantics of lmcache_engine.retrieve), independently of the others.
+static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, const int32_t* chunk_tokens, int32_t n_chunks,
+                     const int32_t* req_first, int32_t n_reqs, const int64_t* slot_mapping, void* compute_stream,
+                     uint64_t* ticket, int64_t* req_loaded, int32_t layers_per_group) {
+  if (!ctx || !keys || !chunk_tokens || !req_first || !slot_mapping || n_chunks <= 0 || n_reqs <= 0 || !ticket ||
+      layers_per_group < 0)
     return B200KV_EINVAL;
   if (!ctx->pool || !ctx->kv_registered || ctx->stage.empty()) return B200KV_EINVAL;
   const Geometry& g = ctx->g;
-  if (n_chunks != static_cast<int32_t>((n_tokens + g.C - 1) / g.C)) return B200KV_EINVAL;
+  if (req_first[0] != 0 || req_first[n_reqs] != n_chunks) return B200KV_EINVAL;
   DeviceGuard dg(ctx->cfg.device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   reap(ctx);
   cudaStream_t cs = static_cast<cudaStream_t>(compute_stream);
   *ticket = 0;
-  if (n_loaded_tokens) *n_loaded_tokens = 0;
+  if (req_loaded) std::fill(req_loaded, req_loaded + n_reqs, 0);
   {
     const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * g.bs;
-    for (int64_t i = 0; i < n_tokens; ++i)
-      if (slot_mapping[i] < 0 || slot_mapping[i] >= max_slot) return B200KV_EINVAL;  // before pinning anything
+    for (int32_t c = 0; c < n_chunks; ++c) {   // before pinning anything
+      if (chunk_tokens[c] <= 0 || chunk_tokens[c] > static_cast<int32_t>(g.C)) return B200KV_EINVAL;
+      const int64_t* sm = slot_mapping + static_cast<int64_t>(c) * g.C;
+      for (int32_t i = 0; i < chunk_tokens[c]; ++i)
+        if (sm[i] < 0 || sm[i] >= max_slot) return B200KV_EINVAL;
+    }
+    for (int32_t r = 0; r < n_reqs; ++r)
+      if (req_first[r] > req_first[r + 1]) return B200KV_EINVAL;
   }
 
   struct Todo { int32_t c; uint32_t slot; uint32_t n_tok; };
   std::vector<Todo> todo;
-  for (int32_t c = skip_chunks; c < n_chunks; ++c) {
-    const uint32_t want = static_cast<uint32_t>(std::min<int64_t>(g.C, n_tokens - static_cast<int64_t>(c) * g.C));
-    uint32_t slot = 0, fmt = 0;
-    int32_t have = 0;
-    if (b200kv_pool_acquire(ctx->pool, keys[c], &slot, &have, &fmt) != B200KV_OK) break;
-    if (static_cast<uint32_t>(have) != want || fmt != pool_fmt(ctx)) {
-      b200kv_pool_release(ctx->pool, keys[c]);
-      break;
+  for (int32_t r = 0; r < n_reqs; ++r) {
+    for (int32_t c = req_first[r]; c < req_first[r + 1]; ++c) {
+      const uint32_t want = static_cast<uint32_t>(chunk_tokens[c]);
+      uint32_t slot = 0, fmt = 0;
+      int32_t have = 0;
+      if (b200kv_pool_acquire(ctx->pool, keys[c], &slot, &have, &fmt) != B200KV_OK) break;
+      if (static_cast<uint32_t>(have) != want || fmt != pool_fmt(ctx)) {
+        b200kv_pool_release(ctx->pool, keys[c]);
+        break;
+      }
+      todo.push_back({c, slot, want});
+      if (req_loaded) req_loaded[r] += want;
     }
-    todo.push_back({c, slot, want});
   }
   ++ctx->stats.n_load_ops;
   if (todo.empty()) return B200KV_OK;
@@ -1555,18 +1593,47 @@ static int load_impl(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, co
   // chunk-wise: the forward pass must see the loaded pages; layer-wise: it waits per layer instead
   if (!detached && !layerwise) CU_TRY(cudaStreamWaitEvent(cs, op->done, 0));
   ctx->stats.n_loaded_tokens += loaded;
-  if (n_loaded_tokens) *n_loaded_tokens = loaded;
   *ticket = op->id;
   ctx->ops.emplace(op->id, std::move(guard.op));
   guard.armed = false;
   return B200KV_OK;
 }
 
+static int load_single(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks, const int64_t* slot_mapping,
+                       int64_t n_tokens, int32_t skip_chunks, void* compute_stream, uint64_t* ticket,
+                       int64_t* n_loaded_tokens, int32_t layers_per_group) {
+  if (!ctx || !keys || !slot_mapping || n_tokens <= 0 || !ticket || skip_chunks < 0) return B200KV_EINVAL;
+  const int64_t C = ctx->g.C;
+  if (n_chunks != static_cast<int32_t>((n_tokens + C - 1) / C)) return B200KV_EINVAL;
+  if (ticket) *ticket = 0;
+  if (n_loaded_tokens) *n_loaded_tokens = 0;
+  if (skip_chunks >= n_chunks) {      // nothing after the masked prefix: still validate like the general path
+    const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * ctx->g.bs;
+    for (int64_t i = 0; i < n_tokens; ++i)
+      if (slot_mapping[i] < 0 || slot_mapping[i] >= max_slot) return B200KV_EINVAL;
+    return (ctx->pool && ctx->kv_registered && !ctx->stage.empty()) ? B200KV_OK : B200KV_EINVAL;
+  }
+  {   // slots of the masked prefix are validated too (the old single-request contract)
+    const int64_t max_slot = static_cast<int64_t>(ctx->cfg.n_blocks) * ctx->g.bs;
+    for (int64_t i = 0; i < static_cast<int64_t>(skip_chunks) * C && i < n_tokens; ++i)
+      if (slot_mapping[i] < 0 || slot_mapping[i] >= max_slot) return B200KV_EINVAL;
+  }
+  const int32_t n = n_chunks - skip_chunks;
+  std::vector<int32_t> ct(static_cast<size_t>(n));
+  for (int32_t c = 0; c < n; ++c) ct[c] = static_cast<int32_t>(std::min<int64_t>(C, n_tokens - (c + skip_chunks) * C));
+  const int32_t first[2] = {0, n};
+  int64_t loaded = 0;
+  const int rc = load_impl(ctx, keys + skip_chunks, ct.data(), n, first, 1, slot_mapping + static_cast<int64_t>(skip_chunks) * C,
+                           compute_stream, ticket, &loaded, layers_per_group);
+  if (rc == B200KV_OK && n_loaded_tokens) *n_loaded_tokens = loaded;
+  return rc;
+}
+
 extern "C" int b200kv_load_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
                                  const int64_t* slot_mapping, int64_t n_tokens, int32_t skip_chunks,
                                  void* compute_stream, uint64_t* ticket, int64_t* n_loaded_tokens) {
-  return load_impl(ctx, keys, n_chunks, slot_mapping, n_tokens, skip_chunks, compute_stream, ticket,
-                   n_loaded_tokens, 0);
+  return load_single(ctx, keys, n_chunks, slot_mapping, n_tokens, skip_chunks, compute_stream, ticket,
+                     n_loaded_tokens, 0);
 }
 
 extern "C" int b200kv_load_layerwise_async(b200kv_ctx* ctx, const uint64_t* keys, int32_t n_chunks,
@@ -1574,8 +1641,16 @@ extern "C" int b200kv_load_layerwise_async(b200kv_ctx* ctx, const uint64_t* keys
                                            int32_t layers_per_group, void* compute_stream, uint64_t* ticket,
                                            int64_t* n_loaded_tokens) {
   if (layers_per_group <= 0) return B200KV_EINVAL;
-  return load_impl(ctx, keys, n_chunks, slot_mapping, n_tokens, skip_chunks, compute_stream, ticket,
-                   n_loaded_tokens, layers_per_group);
+  return load_single(ctx, keys, n_chunks, slot_mapping, n_tokens, skip_chunks, compute_stream, ticket,
+                     n_loaded_tokens, layers_per_group);
+}
+
+extern "C" int b200kv_load_batch_async(b200kv_ctx* ctx, const uint64_t* keys, const int32_t* chunk_tokens,
+                                       int32_t n_chunks, const int32_t* req_first_chunk, int32_t n_reqs,
+                                       const int64_t* slot_mapping, int32_t layers_per_group, void* compute_stream,
+                                       uint64_t* ticket, int64_t* req_loaded_tokens) {
+  return load_impl(ctx, keys, chunk_tokens, n_chunks, req_first_chunk, n_reqs, slot_mapping, compute_stream, ticket,
+                   req_loaded_tokens, layers_per_group);
 }
 
 extern "C" int b200kv_wait_layer(b200kv_ctx* ctx, uint64_t ticket, int32_t layer, void* compute_stream) {

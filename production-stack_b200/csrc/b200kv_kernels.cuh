@@ -411,8 +411,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
   const uint32_t tb = p.paged.token_bytes;
   const uint32_t win_lo = c * p.chunk_tokens + rank * W;  // op-relative token index
   uint32_t n_valid = 0;
-  if (win_lo < p.n_tokens) n_valid = min(W, p.n_tokens - win_lo);
-  const uint32_t chunk_hi = min((c + 1) * p.chunk_tokens, p.n_tokens);
+  // tokens of this chunk = end of its last run (runs are sorted by b): a batch of several requests may hold
+  // partial chunks anywhere, not only at its end
+  uint32_t chunk_hi = c * p.chunk_tokens;
+  {
+    const uint32_t rr0 = p.chunk_run_off[c], rr1 = p.chunk_run_off[c + 1];
+    if (rr1 > rr0) chunk_hi = static_cast<uint32_t>(p.runs[rr1 - 1].b + p.runs[rr1 - 1].n);
+  }
+  if (win_lo < chunk_hi) n_valid = min(W, chunk_hi - win_lo);
   if (win_lo + n_valid > chunk_hi) n_valid = chunk_hi > win_lo ? chunk_hi - win_lo : 0;
 
   if (threadIdx.x < kMaxHeads) {
@@ -578,8 +584,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
 // Unit of work = (chunk, plane, head): the C x D bf16 elements one scale covers (64 KiB for C=256,
 // D=128), i.e. exactly what has to be seen before anything can be quantised.  Nothing is exchanged
 // between CTAs: no cluster, no DSMEM, no atomics.  One CTA per SM:
-//   warp 0           producer: for every unit one TMA copy per paged block ([bs][D] of head h, 4 KiB) into
-//                    a kS3Stages-deep ring of unit buffers, completion on the stage's `full` mbarrier.
+//   warp 0           producer: for every unit one TMA copy per paged block ([bs][D] of head h, 4 KiB) into the
+//                    unit buffer of the consumer group that will take it, completion on its `full` mbarrier.
 //                    HND tiles: the piece is contiguous -> cp.async.bulk (UBLKCP).  NHD tiles: the piece is
 //                    bs rows of D elements strided by the token size -> cp.async.bulk.tensor.4d through a
 //                    per-plane tensor map {D, H, bs, NB}, box {D, 1, bs, 1} (UTMALDG).  Either way the unit
@@ -588,14 +594,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
 //                    (16 x 16 B per thread, conflict-free), release the stage at once (`empty`), absmax
 //                    (packed u16 max, one REDUX per warp, one named barrier per group), quantise from
 //                    registers, 8-byte stores that fill whole 128-byte lines.
-// While one group reduces and quantises, the other group's loads and two more stages are in flight, so the
-// memory pipe never drains between the load -> absmax -> quantise phases of a unit (the cluster kernel above
+// A group releases its buffer as soon as the unit is in registers, so while it reduces and quantises unit i its
+// unit i+2 is already streaming in, and so is the other group's: the memory pipe never drains between the load -> absmax -> quantise phases of a unit (the cluster kernel above
 // runs at 33 % warps active with exactly that bubble).  HBM is read once and written once.
 // Eligibility (checked on the host, else the cluster kernel runs): every chunk is a sequence of whole,
 // block-aligned runs, the last one possibly short — what any vLLM block table produces.
 // ---------------------------------------------------------------------------------------------
-constexpr int kS3Stages = 3;
 constexpr int kS3Groups = 2;
+constexpr int kS3Stages = kS3Groups;   // stage g is filled for, and drained by, consumer group g only: consecutive uses of a
+                                       // stage are strictly ordered, so a parity wait can never alias an older phase (with a
+                                       // shared ring a group could ask for use k of a stage whose use k-1 — the OTHER group's
+                                       // unit — had not landed yet, pass on the parity of use k-2 and corrupt the barrier)
 constexpr int kS3GroupThreads = 256;
 constexpr int kS3Threads = 32 + kS3Groups * kS3GroupThreads;
 constexpr int kS3MaxVec = 16;          // 16-byte vectors per consumer thread per unit
@@ -661,7 +670,7 @@ __global__ void __launch_bounds__(kS3Threads, 1) kv_fp8_store3_kernel(const Fp8S
       const uint32_t h = u % H;
       const uint32_t plane = (u / H) % p.n_planes;
       const uint32_t c = u / (H * p.n_planes);
-      const uint32_t s = i % kS3Stages, k = i / kS3Stages;
+      const uint32_t s = i % kS3Groups, k = i / kS3Groups;    // stage == consumer group; k-th use of that stage
       const uint32_t r0 = __ldg(p.chunk_run_off + c), r1 = __ldg(p.chunk_run_off + c + 1);
       const uint32_t n_blocks = r1 - r0;
       if (k > 0) mbar_wait(&empty_bar[s], (k - 1) & 1);
@@ -700,8 +709,10 @@ __global__ void __launch_bounds__(kS3Threads, 1) kv_fp8_store3_kernel(const Fp8S
     const uint32_t h = u % H;
     const uint32_t plane = (u / H) % p.n_planes;
     const uint32_t c = u / (H * p.n_planes);
-    const uint32_t s = i % kS3Stages, k = i / kS3Stages;
-    const uint32_t n_valid = min(p.chunk_tokens, p.n_tokens - c * p.chunk_tokens);
+    const uint32_t s = g, k = it;
+    // run j of the chunk is its paged block j, all full but possibly the last (host-checked)
+    const uint32_t cr0 = __ldg(p.chunk_run_off + c), cr1 = __ldg(p.chunk_run_off + c + 1);
+    const uint32_t n_valid = (cr1 - cr0 - 1) * bs + static_cast<uint32_t>(p.runs[cr1 - 1].n);
     const uint8_t* stage = smem + static_cast<size_t>(s) * unit_bytes;
 
     mbar_wait(&full_bar[s], k & 1);
@@ -782,8 +793,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(256, 4)
   const uint32_t bs = p.paged.block_tokens;
   const uint32_t win_lo = c * p.chunk_tokens + rank * W;
   uint32_t n_valid = 0;
-  if (win_lo < p.n_tokens) n_valid = min(W, p.n_tokens - win_lo);
-  const uint32_t chunk_hi = min((c + 1) * p.chunk_tokens, p.n_tokens);
+  // tokens of this chunk = end of its last run (runs are sorted by b): a batch of several requests may hold
+  // partial chunks anywhere, not only at its end
+  uint32_t chunk_hi = c * p.chunk_tokens;
+  {
+    const uint32_t rr0 = p.chunk_run_off[c], rr1 = p.chunk_run_off[c + 1];
+    if (rr1 > rr0) chunk_hi = static_cast<uint32_t>(p.runs[rr1 - 1].b + p.runs[rr1 - 1].n);
+  }
+  if (win_lo < chunk_hi) n_valid = min(W, chunk_hi - win_lo);
   if (win_lo + n_valid > chunk_hi) n_valid = chunk_hi > win_lo ? chunk_hi - win_lo : 0;
 
   if (threadIdx.x < kMaxHeads) {

@@ -430,3 +430,63 @@ def test_scheduler_and_worker_use_key_tokens_end_to_end():
     assert turn("b", feat_b, list(range(12, 24))) == C            # only the chunk before the image is reusable
     assert turn("a2", feat_a, list(range(24, 36))) == 3 * C - 1   # full hit minus the recomputed last token
     assert not sched.identities                                    # dropped with the finished requests
+
+
+# ---- one engine op per step: the requests of a step are handed to the engine together --------------------------
+class BatchingEngine(OracleBackedEngine):
+    """OracleBackedEngine + KVEngine's batch calls (same semantics, per request, through the oracle)."""
+
+    def store_batch(self, reqs, stream=None):
+        self.calls.append(("store_batch", [(len(t), off) for t, _sm, off in reqs]))
+        for t, sm, off in reqs:
+            mask = np.ones(len(t), bool)
+            mask[:off] = False
+            self.oe.store(t, mask, self.layers, sm, off)
+        return 5
+
+    def retrieve_batch(self, reqs, stream=None, layers_per_group=0):
+        self.calls.append(("retrieve_batch", [(len(t), skip) for t, _sm, skip in reqs], layers_per_group))
+        got = []
+        for t, sm, skip in reqs:
+            mask = np.ones(len(t), bool)
+            mask[:skip] = False
+            got.append(int(self.oe.retrieve(t, mask, self.layers, sm).sum()))
+        return np.asarray(got, dtype=np.int64), 9
+
+
+def test_requests_of_one_step_share_one_engine_op():
+    rng = np.random.default_rng(21)
+    layers = [rng.integers(0, 2 ** 16, (2, 96, BS, 2, 8), dtype=np.uint16) for _ in range(2)]
+    ref_layers = [l.copy() for l in layers]
+    eng, ref = BatchingEngine(layers), OracleBackedEngine(ref_layers)
+    w, wr = WorkerState(eng, BS, C), WorkerState(ref, BS, C)
+    prompts = [list(rng.integers(0, 1000, n)) for n in (2 * C + 5, C, 3 * C + 17)]
+    blocks = [list(range(0, 9)), list(range(9, 13)), list(range(13, 27))]
+    from b200kv.adapter import SaveSpec
+    metas = lambda: [ReqMeta(f"r{i}", np.asarray(p, np.int32), b, is_last_prefill=True, save_spec=SaveSpec(0, True))  # noqa: E731
+                     for i, (p, b) in enumerate(zip(prompts, blocks))]
+    w.save(metas())
+    wr.save(metas())
+    assert [c[0] for c in eng.calls] == ["store_batch"] and len(eng.calls[0][1]) == 3      # ONE op for three requests
+    assert [c[0] for c in ref.calls] == ["store"] * 3
+    assert w.stats.num_stored_tokens == wr.stats.num_stored_tokens == sum(map(len, prompts))
+    assert w.pending_tickets == [5]
+    for p in prompts:
+        assert eng.oe.lookup(p) == ref.oe.lookup(p) == len(p)
+    # load them into other pages, the third one after a masked (vLLM-cached) first chunk; a fourth request misses
+    for l in layers + ref_layers:
+        l[:] = 0
+    dst = [list(range(40, 49)), list(range(49, 53)), list(range(53, 67)), list(range(70, 74))]
+    miss = list(rng.integers(2000, 3000, C + 3))
+    load_metas = lambda: [ReqMeta(f"l{i}", np.asarray(p, np.int32), b, load_spec=LoadSpec(C if i == 2 else 0, len(p), True))  # noqa: E731
+                          for i, (p, b) in enumerate(zip(prompts + [miss], dst))]
+    w.start_load(load_metas(), layers_per_group=2)
+    wr.start_load(load_metas(), layers_per_group=2)
+    assert eng.calls[-1][0] == "retrieve_batch" and eng.calls[-1][1] == [(len(prompts[0]), 0), (C, 0), (len(prompts[2]), C),
+                                                                       (len(miss), 0)] and eng.calls[-1][2] == 2
+    assert w.stats.num_loaded_tokens == wr.stats.num_loaded_tokens == sum(map(len, prompts)) - C
+    assert w.stats.num_load_shortfalls == wr.stats.num_load_shortfalls == 1
+    assert w.take_load_errors() == wr.take_load_errors() == set(dst[3][:(len(miss) + BS - 1) // BS])
+    assert len(w.layer_loads) == 1 and w.layer_loads[0][0] == 9            # one ticket the forward pass waits on per layer
+    for a, b in zip(layers, ref_layers):
+        assert np.array_equal(a, b)

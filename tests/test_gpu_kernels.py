@@ -673,3 +673,73 @@ def test_refused_op_leaves_no_reserved_slots_and_no_pins():
     assert pool.clear()                                      # ... none of which stayed pinned (clear() fails with pins)
     eng.close()
     pool.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# One engine op for the requests of a step (b200kv_store_batch_async / b200kv_load_batch_async): same bytes in
+# the pool and in the pages as one op per request, for every format and tile order; partial chunks sit in the
+# MIDDLE of a batch (every request's ragged tail), each request stops at its own first miss.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hnd", [False, True])
+@pytest.mark.parametrize("fmt", [FMT_RAW, FMT_FP8, b200kv.FMT_Q4])
+@pytest.mark.parametrize("layerwise", [0, 2])
+def test_batch_ops_equal_per_request_ops_and_oracle(fmt, hnd, layerwise):
+    need_gpu()
+    p = SMALL
+    rng = np.random.default_rng(77 + fmt)
+    host = mk_host_layers(rng, p["L"], p["NB"], p["bs"], p["H"], p["D"])
+    dev = to_dev_hnd(host) if hnd else to_dev(host)
+    stride = 2 * p["bs"] * p["H"] * p["D"] * 2 if hnd else 0
+    geom = KVGeometry(p["L"], p["H"], p["D"], p["NB"], p["bs"], p["C"], 2, stride, fmt,
+                      b200kv._lib.LAYOUT_HND if hnd else b200kv._lib.LAYOUT_NHD)
+    pool = KVPool(None, 16 * geom.chunk_bytes, geom.chunk_bytes, 1)
+    eng = KVEngine(geom, pool, 0, staging_bytes=8 * geom.chunk_bytes)
+    eng.register_kv_caches(dev)
+    name = {FMT_RAW: "raw", FMT_FP8: "fp8", b200kv.FMT_Q4: "q4"}[fmt]
+    oe = ko.OracleEngine(p["C"], name)
+    C_, bs = p["C"], p["bs"]
+    lens = [C_ + 37, 5, 2 * C_, 3 * C_ - 1]                 # ragged tails in the middle of the batch
+    perm = rng.permutation(p["NB"])
+    toks, sms, o = [], [], 0
+    for n in lens:
+        nb = (n + bs - 1) // bs
+        toks.append(rng.integers(0, 128256, n).astype(np.int32))
+        sms.append(ko.slot_mapping_from_blocks(perm[o:o + nb], bs, n))
+        o += nb
+    # request 3 is stored from its second chunk on (offset = C): its first chunk stays a miss
+    offs = [0, 0, 0, C_]
+    t = eng.store_batch(list(zip(toks, sms, offs)))
+    assert t != 0
+    eng.wait(t)
+    assert eng.stats()["n_store_ops"] == 1
+    for tk, sm, off in zip(toks, sms, offs):
+        m = np.ones(len(tk), bool)
+        m[:off] = False
+        oe.store(tk, m, host, sm, off)
+    assert [eng.lookup(tk) for tk in toks] == [oe.lookup(tk) for tk in toks] == [lens[0], lens[1], lens[2], 0]
+    # load: other pages; request 2 with its first chunk masked; request 3 misses at once (chunk 0 absent)
+    dperm = rng.permutation(p["NB"])
+    dms, o = [], 0
+    for n in lens:
+        nb = (n + bs - 1) // bs
+        dms.append(ko.slot_mapping_from_blocks(dperm[o:o + nb], bs, n))
+        o += nb
+    for tns in dev:
+        tns.zero_()
+    skips = [0, 0, C_, 0]
+    got, ticket = eng.retrieve_batch(list(zip(toks, dms, skips)), layers_per_group=layerwise)
+    if layerwise:
+        for l in range(0, p["L"], layerwise):
+            eng.wait_layer(ticket, l)
+    torch.cuda.synchronize()
+    assert list(got) == [lens[0], lens[1], lens[2] - C_, 0]
+    assert eng.stats()["n_load_ops"] == 1
+    dst = [np.zeros_like(l) for l in host]
+    for tk, dm, sk in zip(toks, dms, skips):
+        m = np.ones(len(tk), bool)
+        m[:sk] = False
+        oe.retrieve(tk, m, dst, dm)
+    for a, b in zip(dev, dst):
+        assert np.array_equal(logical_bits(a) if hnd else bits_of(a), b)
+    eng.close()
+    pool.close()

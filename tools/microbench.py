@@ -113,6 +113,31 @@ def main():
                 c, k = timed(lambda i: eng.scatter(dst[i % len(dst)], buf.data_ptr()), args.warmup, args.iters,
                              lambda: eng.last_kernel_ms(1))
                 add(n_tok, fmt, layout, "retrieve(scatter)", c, k, "b200kv")
+            # one engine op per step: 16 requests x 256 tokens handed over together (b200kv_store_batch_async /
+            # b200kv_load_batch_async build exactly this table) vs one op per request
+            n_req, small = 16, 256
+            wins = windows(perm, small, 512)
+            dwins = windows(dperm, small, 512)
+
+            def group(ws, i):
+                return [slots_of(ws[(i * n_req + j) % len(ws)]) for j in range(n_req)]
+
+            def per_request(i, ws, fn):
+                for j, sm in enumerate(group(ws, i)):
+                    fn(sm, buf.data_ptr() + j * geom.chunk_bytes)
+
+            for op, ws, fn, which in (("store(gather)", wins, eng.gather, 0), ("retrieve(scatter)", dwins, eng.scatter, 1)):
+                c1, _ = timed(lambda i: per_request(i, ws, fn), 5, max(10, args.iters // 4))
+                c2, k2 = timed(lambda i: fn(np.concatenate(group(ws, i)), buf.data_ptr()), 5, max(10, args.iters // 4),
+                               lambda: eng.last_kernel_ms(which))
+                algo = ALGO[fmt] * small * n_req
+                r = {"n_tok": small, "requests_per_step": n_req, "format": FMT_NAME[fmt], "tile": layout, "op": op,
+                     "impl": "b200kv", "one_op_per_request_call_ms": round(c1, 4), "one_op_per_step_call_ms": round(c2, 4),
+                     "one_op_per_step_kernel_ms": round(k2, 4), "per_request_call_us_batched": round(c2 / n_req * 1e3, 2),
+                     "per_request_call_us_unbatched": round(c1 / n_req * 1e3, 2),
+                     "kernel_GBps_batched": round(algo / k2 / 1e6, 1), "frac_of_hbm_peak": round(algo / k2 / 1e6 / peak, 3)}
+                rows.append(r)
+                print(json.dumps(r), flush=True)
             eng.close()
             del buf
         if layout == "NHD" and not args.no_torch_baseline:
