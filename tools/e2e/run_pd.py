@@ -67,23 +67,26 @@ async def stream_completion(session, url, body):
     return (first or time.time()) - t0, "".join(text)
 
 
-async def drive(args, p_urls, d_urls):
+async def drive(args, p_urls, d_urls, ref_urls=None):
+    """ref_urls: engines WITHOUT a KV connection to the P/D engines for the single-engine reference (when P and D
+    share one pinned pool, a reference run on D would put the prompt's KV where P's prefill finds it)."""
     rows = []
     timeout = aiohttp.ClientTimeout(total=600)
     sem = asyncio.Semaphore(max(1, args.concurrency))
     async with aiohttp.ClientSession(timeout=timeout) as s:
         async def one(i):
             async with sem:
-                rows.append(await one_request(args, s, i, p_urls[i % len(p_urls)], d_urls[i % len(d_urls)]))
+                rows.append(await one_request(args, s, i, p_urls[i % len(p_urls)], d_urls[i % len(d_urls)],
+                                              ref_urls[i % len(ref_urls)] if ref_urls else None))
         await asyncio.gather(*[one(i) for i in range(args.requests)])
     return rows
 
 
-async def one_request(args, s, i, p_url, d_url):
+async def one_request(args, s, i, p_url, d_url, ref_url=None):
     prompt = f"request {i} " + " ".join(["hi"] * args.prompt_words)
     base = {"model": MODEL, "prompt": prompt, "max_tokens": args.max_tokens, "temperature": 0}
     # reference: one engine does everything (decode engine, no hand-off)
-    ref_ttft, ref_text = await stream_completion(s, d_url + "/v1/completions", dict(base, stream=True))
+    ref_ttft, ref_text = await stream_completion(s, (ref_url or d_url) + "/v1/completions", dict(base, stream=True))
     # step 1: prefill
     t0 = time.time()
     pre = dict(base, max_tokens=1, stream=False,

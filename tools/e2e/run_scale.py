@@ -288,7 +288,8 @@ def pd_direct(box: Box, p_gpus: list[int], d_gpus: list[int], results: list):
     res = {"experiment": "pd_direct", "prefill_gpus": p_gpus, "decode_gpus": d_gpus}
     try:
         t_start = time.time()
-        rows = asyncio.run(run_pd.drive(args, p_urls, d_urls))
+        ref_urls = [f"http://{host_of(g)}:{8100 + g}" for g in d_gpus]    # connector-less engines on the decode GPUs
+        rows = asyncio.run(run_pd.drive(args, p_urls, d_urls, ref_urls))
         res.update(requests=len(rows), prompt_tokens=rows[0]["prompt_tokens"],
                    handoff_params_returned=sum(r["handoff_params"] for r in rows),
                    prefill_p50_ms=statistics.median(r["prefill_s"] for r in rows) * 1e3,
