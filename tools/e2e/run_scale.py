@@ -417,7 +417,7 @@ def main():
         if "cross" not in skip and G >= 2:
             # every turn of a conversation lands on ANOTHER replica: its history comes from the peer's HBM (device tier,
             # NVLink, no host hop) — or, with the tier switched off, from the shared pinned pool (one PCIe hop)
-            for name, off in ((f"n{G}_kv_roundrobin_tier", False), (f"n{G}_kv_roundrobin_hostpool", True), (f"n{G}_none_roundrobin", None)):
+            for name, off in ((f"n{G}_kv_roundrobin_tier", False), (f"n{G}_kv_roundrobin_hostpool", True)):
                 if off:
                     open(box.tier_off_file, "w").close()
                 kind = "none" if off is None else "kv"

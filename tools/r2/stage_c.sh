@@ -16,6 +16,6 @@ python tools/prof_tier.py 5 > "$out/tier_noprof.log" 2>&1; tail -2 "$out/tier_no
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus 2 > "$out/bench_n2.json" 2> "$out/bench_n2.err"
 tail -c 1500 "$out/bench_n2.json"
-timeout 1000 python tools/e2e/run_scale.py --gpus 2 --seconds 35 --qps-per-replica 8 --users-per-replica 24 --qps-sweep 4,12,16 \
+timeout 1300 python tools/e2e/run_scale.py --gpus 2 --seconds 35 --qps-per-replica 8 --users-per-replica 24 --qps-sweep 4,12,16 \
     --cpu-gb 20 --pd-requests 8 --log-dir "$out/scale2" 2>&1 | cut -c1-900
 ls "$out" "$out/scale2" | head -60
