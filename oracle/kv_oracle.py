@@ -244,7 +244,7 @@ def fp8_tolerance(x: np.ndarray, scale_per_elem: np.ndarray) -> np.ndarray:
 # q4 group-wise chunk codec (SURVEY.md §8f-4 "sub-8-bit codec"; north_star "optional CacheGen
 # token-chunk quantisation").  SPECIFIED HERE FIRST; the CUDA kernels (kv_q4_store/load_kernel) follow it.
 #   * group = Q4_GROUP consecutive elements along D of one (token, head)
-#   * scale = bf16_rn(absmax / 7); inv = fl32(1 / scale); codes = clamp(rint(fl32(x * inv)), -7, 7) as two's-complement nibbles,
+#   * scale = bf16_rn(absmax / 7); inv = fl32(1 / scale); codes = rint(x * inv) (exact product, ties to even; within +-7) as two's-complement nibbles,
 #     element 2i in the low nibble of byte i; absmax == 0 -> scale 1, codes 0
 #   * x_hat = bf16_rn(code * scale)        ->  4 + 16/Q4_GROUP = 4.5 bits per element
 # ---------------------------------------------------------------------------------------------
@@ -260,9 +260,10 @@ def q4_pack_chunk(chunk_bits: np.ndarray):
     s_bits = np.where(amax == 0, f32_to_bf16_bits_rn(np.float32(1.0)),
                       f32_to_bf16_bits_rn((amax / np.float32(7.0)).astype(np.float32)))
     s = bf16_bits_to_f32(s_bits)
-    # one IEEE division per group, then float32 multiplications (what a GPU does at full rate)
+    # one IEEE division per group, then rint of the EXACT product x * inv (a float64 holds it exactly: 24 + 24
+    # mantissa bits) — what one fused multiply-add against 1.5 * 2^23 yields on the GPU.  |x * inv| <= 7 (1 + 2^-8).
     inv = (np.float32(1.0) / s).astype(np.float32)
-    q = np.clip(np.rint((x * inv[..., None]).astype(np.float32)), -7, 7).astype(np.int8)
+    q = np.clip(np.rint(x.astype(np.float64) * inv[..., None].astype(np.float64)), -7, 7).astype(np.int8)
     q = q.reshape(L, two, n, H, D)
     nib = (q & 0xF).astype(np.uint8)
     codes = (nib[..., 0::2] | (nib[..., 1::2] << 4)).astype(np.uint8)

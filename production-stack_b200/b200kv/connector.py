@@ -119,6 +119,13 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
             raise ValueError(f"B200KVConnector supports a single KV-cache group, the model has {len(groups)}: "
                              "start vLLM with --disable-hybrid-kv-cache-manager")
         self.cfg = B200KVConfig.from_env().apply_extra(ktc.kv_connector_extra_config)
+        if role == KVConnectorRole.SCHEDULER and getattr(ktc, "kv_load_failure_policy", "recompute") == "fail":
+            # vLLM's default (config/kv_transfer.py:70).  This connector never raises on the data path: a short or
+            # failed load is REPORTED (get_block_ids_with_load_errors) so that the blocks are recomputed — under the
+            # default policy vLLM fails such a request instead.
+            logger.warning('b200kv: kv_load_failure_policy is "fail": a chunk that is evicted between lookup and load, an '
+                           'expired P/D lease or an unreachable peer will FAIL the request; add '
+                           '"kv_load_failure_policy":"recompute" to --kv-transfer-config to recompute instead')
         self.kv_role = ktc.kv_role
         self._block_size = vllm_config.cache_config.block_size
         self._chunk = self.cfg.chunk_size
@@ -164,8 +171,10 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
                 self._tiers = TierSet(self._engine_id, geom.chunk_bytes, None)
             tiers = self._tiers
 
+            tier_off = os.environ.get("B200KV_TIER_DISABLE_FILE") or None
+
             def lookup(token_ids):
-                if tiers is None:
+                if tiers is None or (tier_off and os.path.exists(tier_off)):   # kill switch: what the host pool holds
                     return pool.lookup_tokens(token_ids, chunk, seed, lease, include_partial)
                 from .device_tier import combined_prefix_tokens
                 from .engine import chunk_keys

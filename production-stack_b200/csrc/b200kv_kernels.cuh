@@ -1044,8 +1044,8 @@ __device__ __forceinline__ void q4_split(uint32_t idx, uint32_t vpt, uint32_t vp
   else { *t = idx / vpt; *v = idx - *t * vpt; }
 }
 
-// q = clamp(rint(x * inv), -7, 7), inv = fl32(1 / s), s = bf16(absmax_group / 7)  (oracle/kv_oracle.py q4_pack_chunk):
-// one IEEE division per group, then multiplications.
+// q = rint(x * inv) (exact product, ties to even), inv = fl32(1 / s), s = bf16(absmax_group / 7)
+// (oracle/kv_oracle.py q4_pack_chunk): one IEEE division per group, then one FMA per element.
 __global__ void __launch_bounds__(256) kv_q4_store_kernel(const Q4Params p) {
   const uint32_t vpt = (p.n_heads * p.head_bytes) >> 4;      // vectors per token (multiple of 4)
   const uint32_t vpt_shift = (vpt & (vpt - 1)) == 0 ? 31u - __clz(vpt) : 0xffffffffu;
@@ -1079,14 +1079,17 @@ __global__ void __launch_bounds__(256) kv_q4_store_kernel(const Q4Params p) {
         const float amax = __uint_as_float(m << 16);
         const __nv_bfloat16 sb = m ? __float2bfloat16_rn(__fdiv_rn(amax, 7.0f)) : __float2bfloat16_rn(1.0f);
         const float inv = __fdiv_rn(1.0f, __bfloat162float(sb));
+        // rint(x * inv) for |x * inv| <= 7.03 without a convert: fma(x, inv, 1.5 * 2^23) rounds the EXACT product to
+        // the nearest integer (ties to even) into the low mantissa bits, whose low nibble is the two's-complement
+        // code.  No clamp is needed: |x| <= absmax and scale >= absmax / 7 * (1 - 2^-9).
         const uint32_t w[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
         uint32_t packed = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
-          const int ql = max(-7, min(7, __float2int_rn(__fmul_rn(lo, inv))));
-          const int qh = max(-7, min(7, __float2int_rn(__fmul_rn(hi, inv))));
-          packed |= (static_cast<uint32_t>(ql & 0xF) | (static_cast<uint32_t>(qh & 0xF) << 4)) << (8 * i);
+          const uint32_t ql = __float_as_uint(__fmaf_rn(lo, inv, 12582912.0f)) & 0xFu;
+          const uint32_t qh = __float_as_uint(__fmaf_rn(hi, inv, 12582912.0f)) & 0xFu;
+          packed |= (ql | (qh << 4)) << (8 * i);
         }
         if (!ok[j]) continue;
         uint8_t* rec = slab + static_cast<uint64_t>(t0 + tt[j]) * p.rec_bytes;

@@ -61,7 +61,7 @@ def model_store(planes, runs, n_chunks, hnd):
                         ko.f32_to_bf16_bits_rn(np.array([1.0], np.float32))[0]
                     s = ko.bf16_bits_to_f32(np.array([sb], np.uint16))[0]
                     xf = ko.bf16_bits_to_f32(x)
-                    q = np.clip(np.rint((xf * (np.float32(1.0) / s)).astype(np.float32)), -7, 7).astype(np.int64)
+                    q = np.clip(np.rint(xf.astype(np.float64) * np.float64(np.float32(1.0) / s)), -7, 7).astype(np.int64)
                     packed = 0
                     for i in range(4):
                         packed |= ((int(q[2 * i]) & 0xF) | ((int(q[2 * i + 1]) & 0xF) << 4)) << (8 * i)

@@ -58,9 +58,9 @@ def main():
     ktc = None
     if a.connector == "native":
         ktc = KVTransferConfig(kv_connector="B200KVConnector", kv_connector_module_path="b200kv.connector",
-                               kv_role="kv_both")
+                               kv_role="kv_both", kv_load_failure_policy="recompute")
     elif a.connector == "alias":
-        ktc = KVTransferConfig(kv_connector="LMCacheConnectorV1", kv_role="kv_both")
+        ktc = KVTransferConfig(kv_connector="LMCacheConnectorV1", kv_role="kv_both", kv_load_failure_policy="recompute")
     kw = {}
     if a.connector == "alias":
         kw["disable_hybrid_kv_cache_manager"] = True     # the wrapper is not SupportsHMA

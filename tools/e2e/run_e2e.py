@@ -43,7 +43,8 @@ def connector_args(mode: str, cpu_gb: float):
                    B200KV_FORMAT="q4" if "q4" in mode else ("fp8" if "8" in mode.replace("c64", "") else "raw"),
                    B200KV_ASYNC_LOAD="1" if "async" in mode else "0",
                    B200KV_LAYERWISE="0" if "cw" in mode else "1")
-        cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}
+        cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both",
+               "kv_load_failure_policy": "recompute"}
         return ["--kv-transfer-config", json.dumps(cfg)], env
     if mode == "offload":
         cfg = {"kv_connector": "OffloadingConnector", "kv_role": "kv_both",
@@ -126,6 +127,7 @@ def main():
     args = ap.parse_args()
     if args.harness and harness_path() is None:
         raise SystemExit("--harness: the reference harness is neither under /root/reference nor in baseline/_ref")
+    args.log_dir = os.path.abspath(args.log_dir)     # the harness runs with another cwd
     os.makedirs(args.log_dir, exist_ok=True)
     subprocess.run([sys.executable, os.path.join(HERE, "make_model.py"), args.model_dir, "--layers", str(args.layers),
                     "--max-len", str(max(args.max_model_len, 8192))], check=True, stdout=subprocess.DEVNULL)

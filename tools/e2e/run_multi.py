@@ -75,7 +75,8 @@ def replica_env(mode: str, gpu: int, cpu_gb: float, pool_tag: str) -> tuple[dict
         env["LMCACHE_REMOTE_URL"] = "lm://127.0.0.1:8095"
     if mode.startswith("tier"):
         env["B200KV_DEVICE_TIER_GB"] = "8"
-    cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}
+    cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both",
+               "kv_load_failure_policy": "recompute"}
     return env, ["--kv-transfer-config", json.dumps(cfg)]
 
 
@@ -126,6 +127,7 @@ def main():
     ap.add_argument("--harness-time", type=float, default=60.0)
     ap.add_argument("--mock", action="store_true", help="orchestration dry run: tools/mock_backend.py instead of vllm (no GPU)")
     args = ap.parse_args()
+    args.log_dir = os.path.abspath(args.log_dir)     # the harness runs with another cwd
     os.makedirs(args.log_dir, exist_ok=True)
     if not args.mock:
         subprocess.run([sys.executable, os.path.join(HERE, "make_model.py"), args.model_dir, "--layers", str(args.layers),

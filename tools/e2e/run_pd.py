@@ -41,7 +41,8 @@ def start_server(gpu: int, port: int, model_dir: str, max_len: int, log_path: st
     env["CUDA_VISIBLE_DEVICES"] = str(gpu)
     env["PYTHONPATH"] = os.path.join(ROOT, "production-stack_b200") + os.pathsep + env.get("PYTHONPATH", "")
     env.update(LMCACHE_LOCAL_CPU="True", LMCACHE_MAX_LOCAL_CPU_SIZE="20", LMCACHE_CHUNK_SIZE="256")
-    cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}
+    cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both",
+               "kv_load_failure_policy": "recompute"}
     cmd = [sys.executable, "-m", "vllm.entrypoints.openai.api_server", "--model", model_dir,
            "--served-model-name", "synth-llama3-8b", "--load-format", "dummy", "--dtype", "bfloat16",
            "--max-model-len", str(max_len), "--no-enable-prefix-caching", "--gpu-memory-utilization", "0.8",

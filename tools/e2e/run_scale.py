@@ -85,7 +85,10 @@ class Box:
                        LMCACHE_ENABLE_CONTROLLER="True", LMCACHE_CONTROLLER_PULL_URL="127.0.0.1:9000",
                        LMCACHE_LMCACHE_WORKER_HEARTBEAT_TIME="2", B200KV_ADVERTISE_IP=host_of(g),
                        B200KV_PD_TRACE=os.path.join(a.log_dir, f"pd_trace_{g}.jsonl"))
-            cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both"}
+            # vLLM's default policy FAILS a request whose load came up short (config/kv_transfer.py:70); the connector's
+            # contract is "report the blocks, vLLM recomputes them"
+            cfg = {"kv_connector": "B200KVConnector", "kv_connector_module_path": "b200kv.connector", "kv_role": "kv_both",
+                   "kv_load_failure_policy": "recompute"}
             cargs = ["--kv-transfer-config", json.dumps(cfg)]
         cmd = [sys.executable, "-m", "vllm.entrypoints.openai.api_server", "--model", a.model_dir,
                "--served-model-name", self.model_name, "--load-format", "dummy", "--dtype", "bfloat16",
@@ -164,8 +167,7 @@ class Box:
 
 
 # -------------------------------------------------------------------------------------------------- traffic
-def summarize_csv(path: str) -> dict:
-    rows = list(csv.DictReader(open(path))) if os.path.exists(path) else []
+def summarize_rows(rows: list[dict]) -> dict:
     if not rows:
         return {"requests": 0}
     ttft = sorted(float(r["ttft"]) for r in rows)
@@ -181,24 +183,43 @@ def summarize_csv(path: str) -> dict:
 
 def run_harness(box: Box, base_url: str, n_rep: int, tag: str, init_uid: int, qps_per_replica: float | None = None,
                 seconds: float | None = None) -> dict:
-    """The unmodified harness; p50 from the CSV it writes (it prints the mean, multi-round-qa.py:497,526)."""
+    """The unmodified harness; p50 from the CSV it writes (it prints the mean, multi-round-qa.py:497,526).  One harness
+    process is a single asyncio loop: from 8 replicas on, the load is offered by two processes (disjoint user ids,
+    half of the users and of the qps each) and their CSVs are merged."""
     a = box.a
     hp = harness_path()
-    out_csv = os.path.join(a.log_dir, f"harness_{tag}.csv")
     qps = (qps_per_replica or a.qps_per_replica) * n_rep
     users = max(2, int(round(a.users_per_replica * n_rep)))
-    cmd = [sys.executable, hp, "--num-users", str(users), "--num-rounds", str(a.num_rounds), "--qps", str(qps),
-           "--shared-system-prompt", str(a.shared_system_prompt), "--user-history-prompt", str(a.user_history_prompt),
-           "--answer-len", str(a.answer_len), "--model", box.model_name, "--base-url", base_url,
-           "--time", str(int(seconds or a.seconds)), "--request-with-user-id", "--init-user-id", str(init_uid),
-           "--output", out_csv]
+    k = max(1, n_rep // 4)
+    procs, csvs = [], []
     t0 = time.time()
-    p = subprocess.run(cmd, capture_output=True, text=True, cwd=a.log_dir, timeout=(seconds or a.seconds) + 240)
-    res = summarize_csv(out_csv)
-    res.update(driver="unmodified multi-round-qa.py", harness_exit=p.returncode, wall_s=time.time() - t0, qps_offered=qps,
-               users=users)
-    if p.returncode:
-        res["harness_tail"] = (p.stdout + p.stderr)[-500:]
+    for j in range(k):
+        out_csv = os.path.join(a.log_dir, f"harness_{tag}_{j}.csv" if k > 1 else f"harness_{tag}.csv")
+        csvs.append(out_csv)
+        cmd = [sys.executable, hp, "--num-users", str(max(2, users // k)), "--num-rounds", str(a.num_rounds), "--qps", str(qps / k),
+               "--shared-system-prompt", str(a.shared_system_prompt), "--user-history-prompt", str(a.user_history_prompt),
+               "--answer-len", str(a.answer_len), "--model", box.model_name, "--base-url", base_url,
+               "--time", str(int(seconds or a.seconds)), "--request-with-user-id", "--init-user-id", str(init_uid + j * 5000),
+               "--output", out_csv]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=a.log_dir))
+    tails, rc = [], 0
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=(seconds or a.seconds) + 240)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        rc = rc or p.returncode
+        tails.append((out or "")[-400:])
+    rows = []
+    for c in csvs:
+        if os.path.exists(c):
+            rows += list(csv.DictReader(open(c)))
+    res = summarize_rows(rows)
+    res.update(driver="unmodified multi-round-qa.py" + (f" x{k} processes" if k > 1 else ""), harness_exit=rc,
+               wall_s=time.time() - t0, qps_offered=qps, users=users)
+    if rc:
+        res["harness_tail"] = tails
     return res
 
 
@@ -350,6 +371,7 @@ def main():
     ap.add_argument("--mock", action="store_true")
     ap.add_argument("--log-dir", default=os.path.join(ROOT, "gpurun_out", "scale"))
     a = ap.parse_args()
+    a.log_dir = os.path.abspath(a.log_dir)      # the harness runs with another cwd
     os.makedirs(a.log_dir, exist_ok=True)
     skip = set(a.skip.split(",")) if a.skip else set()
     if True:      # also for --mock: the kv-aware router loads the tokenizer from this directory
@@ -374,14 +396,30 @@ def main():
             uid[0] += 10000
             return uid[0]
 
+        sweep = [float(x) for x in a.qps_sweep.split(",")] if a.qps_sweep else []
+
+        def sweep_pair(q, g_none, g_kv, port):
+            return [dict(name=f"sweep_q{q:g}_none", kind="none", gpus=[g_none], routing="roundrobin", rport=port, uid=nu(),
+                         qps_per_replica=q), dict(name=f"sweep_q{q:g}_kv", kind="kv", gpus=[g_kv], routing="roundrobin",
+                                                  rport=port + 1, uid=nu(), qps_per_replica=q)]
+
         if "scale" not in skip:
-            # N = 1, 2 side by side, then 4, then 8 — none and kv on disjoint GPUs wherever they fit
+            # N = 1, 2 side by side, then 4, then 8 — none and kv on disjoint GPUs wherever they fit; on an 8-GPU box the
+            # spare GPUs of the first waves carry the N=1 qps sweep
             if G >= 6:
-                wave(box, results, [
-                    dict(name="n1_none", kind="none", gpus=[0], routing="prefixaware", rport=8090, uid=nu()),
-                    dict(name="n1_kv", kind="kv", gpus=[1], routing="prefixaware", rport=8091, uid=nu()),
-                    dict(name="n2_none", kind="none", gpus=[2, 3], routing="prefixaware", rport=8092, uid=nu()),
-                    dict(name="n2_kv", kind="kv", gpus=[4, 5], routing="prefixaware", rport=8093, uid=nu())])
+                specs = [dict(name="n1_none", kind="none", gpus=[0], routing="prefixaware", rport=8090, uid=nu()),
+                         dict(name="n1_kv", kind="kv", gpus=[1], routing="prefixaware", rport=8091, uid=nu()),
+                         dict(name="n2_none", kind="none", gpus=[2, 3], routing="prefixaware", rport=8092, uid=nu()),
+                         dict(name="n2_kv", kind="kv", gpus=[4, 5], routing="prefixaware", rport=8093, uid=nu())]
+                if G >= 8 and sweep:
+                    specs += sweep_pair(sweep.pop(0), 6, 7, 8094)
+                wave(box, results, specs)
+                if sweep and "sweep" not in skip:      # the remaining sweep points, up to four at a time
+                    specs = []
+                    for j, q in enumerate(sweep[:G // 2]):
+                        specs += sweep_pair(q, 2 * j, 2 * j + 1, 8090 + 2 * j)
+                    sweep = sweep[G // 2:]
+                    wave(box, results, specs)
             elif G >= 2:
                 wave(box, results, [dict(name="n1_none", kind="none", gpus=[0], routing="prefixaware", rport=8090, uid=nu()),
                                     dict(name="n1_kv", kind="kv", gpus=[1], routing="prefixaware", rport=8091, uid=nu())])
@@ -400,15 +438,10 @@ def main():
                 allg = list(range(8))
                 for kind in ("none", "kv"):
                     wave(box, results, [dict(name=f"n8_{kind}", kind=kind, gpus=allg, routing="prefixaware", rport=8090, uid=nu())])
-                wave(box, results, [dict(name="n8_kv_session", kind="kv", gpus=allg, routing="session", rport=8090, uid=nu())])
         allg = list(range(G))
-        if "sweep" not in skip and a.qps_sweep and G >= 2:
-            for q in [float(x) for x in a.qps_sweep.split(",")]:
-                wave(box, results, [
-                    dict(name=f"sweep_q{q:g}_none", kind="none", gpus=[0], routing="roundrobin", rport=8090, uid=nu(), qps_per_replica=q,
-                         seconds=min(a.seconds, 30)),
-                    dict(name=f"sweep_q{q:g}_kv", kind="kv", gpus=[1], routing="roundrobin", rport=8091, uid=nu(), qps_per_replica=q,
-                         seconds=min(a.seconds, 30))])
+        if "sweep" not in skip and G >= 2:
+            for q in sweep:      # whatever did not fit beside the scaling waves
+                wave(box, results, sweep_pair(q, 0, 1, 8090))
         if "kvaware" not in skip and G >= 2:
             # configs[3]: kv-aware routing through the compat controller; /v1/completions so the router's lookup sees the
             # engine's tokens

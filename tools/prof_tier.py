@@ -39,6 +39,8 @@ probe = torch.empty(16, dtype=torch.uint8, device="cuda:0")
 probe.copy_(tier[:16])                       # torch enables peer access 0 <-> 1 on first cross-device copy
 cons = KVEngine(geom, None, 0, staging_bytes=0)
 cons.register_kv_caches(local_pages)
+# in-process stand-in for the CUDA-IPC import a real consumer does: maps GPU 1 into GPU 0's context (peer access)
+cons.import_peer_ptrs(1, 1, [t[0].data_ptr() for t in owner_pages], [t[1].data_ptr() for t in owner_pages])
 ptrs = np.array([tier.data_ptr() + i * geom.chunk_bytes for i in range(n_chunks)], dtype=np.uint64)
 torch.cuda.set_device(0)
 for _ in range(reps):
