@@ -209,3 +209,42 @@ def test_reference_router_unit_tests_pass_on_top_of_the_stubs():
                           os.path.join(REF_SRC, "tests", "test_roundrobin_router.py")],
                          env=env, capture_output=True, text=True, timeout=300, cwd="/tmp")
     assert out.returncode == 0 and " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-2000:]
+
+
+def test_prefix_aware_router_concentrates_a_shared_system_prompt_on_one_backend(tmp_path):
+    """Characterisation of the UNMODIFIED reference router (routing_logic.py:447-507, prefix/hashtrie.py:46-104) on
+    the multi-round-QA harness's traffic shape: every conversation starts with the same system prompt, so the trie's
+    deepest match always leads to the backend that served the first request — 'N replicas, prefix-aware' is one
+    replica carrying everything.  This is what the N = 2 / 4 / 8 prefix-aware rows of profiles/scale_8gpu_r02.json
+    show on real engines (1 376 of 1 394 requests on one replica); kept here so the finding stays reproducible
+    without a GPU.  Nothing of this repository is on the routing path."""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "e2e"))
+    import mrqa_driver
+    ps = Procs()
+    try:
+        ports = [free_port() for _ in range(4)]
+        for p in ports:
+            ps.start([sys.executable, os.path.join(ROOT, "tools", "mock_backend.py"), "--port", str(p), "--model", "m"])
+        for p in ports:
+            assert wait_http(f"http://127.0.0.1:{p}/health")
+        rport = free_port()
+        log = open(tmp_path / "router.log", "w")
+        ps.start([sys.executable, "-m", "vllm_router.app", "--host", "127.0.0.1", "--port", str(rport),
+                  "--service-discovery", "static",
+                  "--static-backends", ",".join(f"http://127.0.0.1:{p}" for p in ports),
+                  "--static-models", ",".join(["m"] * 4), "--routing-logic", "prefixaware"], env=router_env(), log=log)
+        assert wait_http(f"http://127.0.0.1:{rport}/health", 90), open(tmp_path / "router.log").read()[-2000:]
+        n_users = 24
+        for uid in range(1, n_users + 1):        # first turns of 24 different users, the harness's prompt (multi-round-qa.py:232-251)
+            msgs = [{"role": "user", "content": mrqa_driver.system_prompt(uid, 300, 200) + mrqa_driver.question(1)}]
+            st, _ = post(f"http://127.0.0.1:{rport}/v1/chat/completions",
+                         {"model": "m", "messages": msgs, "max_tokens": 4, "temperature": 0}, {"x-user-id": str(uid)})
+            assert st == 200
+        counts = []
+        for p in ports:
+            with urllib.request.urlopen(f"http://127.0.0.1:{p}/served") as r:
+                counts.append(len(json.loads(r.read().decode())["served"]))
+        assert sum(counts) == n_users
+        assert max(counts) >= n_users - 3, counts      # (almost) everything on ONE of the four backends
+    finally:
+        ps.stop()

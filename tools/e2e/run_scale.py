@@ -15,6 +15,7 @@ swaps ROUTERS — cheap — between experiments.  Experiments of one wave run co
   wave 1   N=1 none | N=1 kv | N=2 none | N=2 kv          (GPUs 0 | 1 | 2-3 | 4-5)     prefixaware, harness
   wave 2   N=4 none | N=4 kv                              (GPUs 0-3 | 4-7)
   wave 3   N=8 none ; wave 4  N=8 kv                                                   configs[2]
+  then     N=G none ; N=G kv with --routing-logic session (balanced; the reference tutorial's setting)
   wave 5   N=8 kv, --routing-logic kvaware, /v1/completions driver                     configs[3]
   wave 6   N=8 kv, roundrobin (every turn lands on another replica): device tier on -> peer-HBM pull over
            NVLink; wave 7: the same with the tier switched off at run time -> shared host pool (one PCIe hop)
@@ -366,7 +367,7 @@ def main():
     ap.add_argument("--pd-prompt-words", type=int, default=8000)
     ap.add_argument("--pd-requests", type=int, default=16)
     ap.add_argument("--qps-sweep", default="", help="comma list of per-replica qps for an N=1 none-vs-kv sweep (2+ GPUs)")
-    ap.add_argument("--skip", default="", help="comma list of waves to skip: scale,kvaware,cross,pd,sweep")
+    ap.add_argument("--skip", default="", help="comma list of waves to skip: scale,session,kvaware,cross,pd,sweep")
     ap.add_argument("--extra", default="")
     ap.add_argument("--mock", action="store_true")
     ap.add_argument("--log-dir", default=os.path.join(ROOT, "gpurun_out", "scale"))
@@ -438,6 +439,13 @@ def main():
                 allg = list(range(8))
                 for kind in ("none", "kv"):
                     wave(box, results, [dict(name=f"n8_{kind}", kind=kind, gpus=allg, routing="prefixaware", rport=8090, uid=nu())])
+        if "session" not in skip and G >= 2:
+            # the routing the reference's own multi-GPU benchmark uses (tutorials/08-benchmark-multi-round-qa-multi-gpu.md:
+            # 71-72): consistent hash of x-user-id — balanced, and a conversation stays on its replica.  (The prefix-aware
+            # router sends a workload with a shared system prompt to ONE replica: profiles/scale_8gpu_r02.json.)
+            for kind in ("none", "kv"):
+                wave(box, results, [dict(name=f"n{G}_{kind}_session", kind=kind, gpus=list(range(G)), routing="session",
+                                         rport=8090, uid=nu())])
         allg = list(range(G))
         if "sweep" not in skip and G >= 2:
             for q in sweep:      # whatever did not fit beside the scaling waves
