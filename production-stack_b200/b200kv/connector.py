@@ -140,7 +140,8 @@ class B200KVConnector(KVConnectorBase_V1, SupportsHMA):
         self._pool_name = pool_name_for(vllm_config, self.cfg, geom.chunk_bytes)
         if role == KVConnectorRole.SCHEDULER:
             try:
-                n_swept = KVPool.sweep(ENGINE_POOL_PREFIX, int(self.cfg.extra.get("sweep_min_age_s", 60)))
+                age = int(self.cfg.extra.get("sweep_min_age_s", 60))
+                n_swept = KVPool.sweep(ENGINE_POOL_PREFIX, age) + KVPool.sweep("/b200kv-dev-", age)   # pools + tier indices
                 if n_swept:
                     logger.warning("b200kv: removed %d pool segment(s) left in /dev/shm by engines that died", n_swept)
             except Exception as e:     # hygiene only
