@@ -127,17 +127,21 @@ class KeyIdentity:
     `request_configs` (the `lmcache.*` kv_transfer_params, adapter :102-117) into the chunk key; vLLM's own
     prefix cache also separates requests by `cache_salt` and LoRA adapter.  Here all of it is folded into
     the token stream the chunk keys are hashed from ("key tokens"): placeholder ranges are overwritten
-    with 128 bits of the item's identifier, and a salted request has every token XORed with a 31-bit salt,
-    so it shares no chunk with an unsalted one or with another salt."""
+    with 128 bits of the item's identifier, and a salted request has its tokens XORed with a 62-bit salt (low
+    31 bits on even positions, high 31 bits on odd ones), so it shares no chunk with an unsalted one or
+    with another salt."""
     salt: int = 0
     spans: list = field(default_factory=list)     # (offset, length, int32[4] words of the item's identifier)
 
     def apply(self, tokens, start: int = 0) -> np.ndarray:
         """Key tokens of `tokens`, which sit at positions [start, start+len) of the request."""
         out = np.array(tokens, dtype=np.int32, copy=True)
-        if self.salt:
-            out ^= np.int32(self.salt)
         n = len(out)
+        if self.salt:
+            even = (start & 1) == 0          # parity of the ABSOLUTE position: windows agree with the whole sequence
+            lo, hi = np.int32(self.salt & 0x7FFFFFFF), np.int32((self.salt >> 31) & 0x7FFFFFFF)
+            out[0::2] ^= lo if even else hi
+            out[1::2] ^= hi if even else lo
         for off, length, words in self.spans:
             lo, hi = max(off, start), min(off + length, start + n)
             if lo < hi:
@@ -180,7 +184,11 @@ def request_identity(req) -> KeyIdentity | None:
         parts.append("tags=" + repr(tags))
     if not spans and not parts:
         return None
-    return KeyIdentity((_hash32("|".join(parts).encode(), 0x6B76) or 1) if parts else 0, spans)
+    salt = 0
+    if parts:
+        from .engine import xxh64
+        salt = (xxh64("|".join(parts).encode(), 0x6B76) & ((1 << 62) - 1)) or 1
+    return KeyIdentity(salt, spans)
 
 
 def request_skip_save(req) -> bool:

@@ -399,6 +399,10 @@ def test_cache_salt_lora_and_tags_isolate_requests():
         kt = ident.apply(prompt)
         assert kt.dtype == np.int32 and (kt >= 0).all() and kt.tobytes() not in seen
         seen.append(kt.tobytes())
+    # a window of the sequence (tokens appended during decode) is salted like the same positions of the whole
+    whole = ident.apply(prompt)
+    for lo_ in (0, 1, C, C + 7):
+        assert np.array_equal(ident.apply(prompt[lo_:lo_ + 33], start=lo_), whole[lo_:lo_ + 33])
     # lmcache.skip_save alone is a save rule, not an identity
     assert request_identity(NS(request_id="r", prompt_token_ids=prompt,
                                sampling_params=NS(extra_args={"kv_transfer_params": {"lmcache.skip_save": True}}))) is None
