@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "production-stack_b200")
 DRIVER = os.path.join(ROOT, "tests", "vllm_inproc_driver.py")
 
-RAW_LOGPROB_TOL = 0.05      # bf16 kernels, different prefill shapes
+RAW_LOGPROB_TOL = 0.08      # bf16 kernels, different prefill shapes (measured: 0.031-0.033)
 FP8_LOGPROB_TOL = 0.4       # nats, on the chosen token of each of the first 4 decode steps (measured: 0.24)
 
 
