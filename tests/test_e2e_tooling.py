@@ -131,3 +131,25 @@ def test_run_e2e_can_drive_with_the_unmodified_harness(tmp_path):
     finally:
         mock.terminate()                  # exactly the process started above
         mock.wait(20)
+
+
+def test_run_scale_dry_run_with_the_unmodified_router_and_harness(tmp_path):
+    """tools/e2e/run_scale.py (the 1/2/4/8-replica session of profiles/scale_8gpu_r02.json) in its orchestration dry
+    run: mock engines started once, routers swapped per wave, the UNMODIFIED harness offering the load (CSV written
+    under another cwd), kv-aware routing through the compat controller, N/2 + N/2 prefill/decode through the router."""
+    if not os.path.exists("/root/reference/benchmarks/multi-round-qa/multi-round-qa.py") and not os.path.exists(
+            os.path.join(ROOT, "baseline", "_ref", "benchmarks", "multi-round-qa", "multi-round-qa.py")):
+        pytest.skip("reference harness not present on this machine")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "e2e", "run_scale.py"), "--gpus", "2", "--mock", "--seconds", "4",
+           "--qps-per-replica", "3", "--users-per-replica", "3", "--num-rounds", "2", "--shared-system-prompt", "20",
+           "--user-history-prompt", "20", "--pd-prompt-words", "40", "--pd-requests", "2", "--skip", "scale,sweep,cross",
+           "--model-dir", str(tmp_path / "model"), "--log-dir", os.path.relpath(tmp_path / "logs")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=os.getcwd())
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = {d["experiment"]: d for d in (json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"experiment"'))}
+    assert {"n2_none_session", "n2_kv_session", "n2_kv_kvaware", "pd_direct", "pd_1p1d_router"} <= set(res)
+    for name in ("n2_none_session", "n2_kv_session"):
+        assert res[name]["requests"] > 0 and res[name]["harness_exit"] == 0 and res[name]["driver"].startswith("unmodified")
+        assert os.path.exists(tmp_path / "logs" / f"harness_{name}.csv")            # a relative --log-dir works
+    assert res["n2_kv_kvaware"]["failed"] == 0 and res["pd_1p1d_router"]["failed"] == 0 and res["pd_direct"]["requests"] == 2
+    assert os.path.exists(tmp_path / "logs" / "scale_results.json")
