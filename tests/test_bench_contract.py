@@ -40,3 +40,21 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def test_numa_maps_reader_and_slot_map_helpers():
+    """bench.py's own small helpers: the /proc/self/numa_maps reader behind `per_rank[].pages_per_node` and the
+    input-table builder that replaced the oracle import in the GPU arm."""
+    import mmap
+    import ctypes
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    buf = mmap.mmap(-1, 8 << 20)
+    buf[:] = b"\x01" * (8 << 20)                      # touch every page
+    addr = ctypes.addressof(ctypes.c_char.from_buffer(buf))
+    nodes = bench.numa_nodes_of(addr + 4096)
+    if os.path.exists("/proc/self/numa_maps"):
+        assert nodes and sum(nodes.values()) >= (8 << 20) // 4096 // 2 and all(k.startswith("N") for k in nodes)
+    sm = bench.slot_map(np.array([5, 2]), 20)
+    assert list(sm[:3]) == [80, 81, 82] and list(sm[16:20]) == [32, 33, 34, 35] and sm.dtype == np.int64
